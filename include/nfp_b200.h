@@ -1,0 +1,149 @@
+/*
+ * nfp_b200.h -- C ABI of the B200-native Neighbourhood Feature Pooling operator.
+ *
+ * This is the drop-in boundary for the NFP hot path.  The reference has no
+ * FFI layer of its own (it is pure PyTorch); the entry points below replace,
+ * one for one, the Python-level operator surface a binding would wrap:
+ *
+ *   nfpb200_forward        <- NFPPooling.forward            (models/pooling/nfp.py:132-134)
+ *                             and the measure it dispatches to (nfp.py:141-374)
+ *   nfpb200_backward       <- autograd through that forward (the reference stores the
+ *                             (B, C*(k*k-1), H', W') neighbour tensor; we recompute)
+ *   nfpb200_pool_forward   <- nfp_pooling.forward up to the projection: GAP(x) and
+ *                             GAP(NFP(x))                   (models/NFP_Pooling.py:27-31)
+ *   nfpb200_pool_backward  <- autograd through those two lines
+ *   nfpb200_output_shape   <- Conv2d output-size rule behind NFPPooling.output_size
+ *                                                           (nfp.py:125-130, 42-47)
+ *   nfpb200_desc_t         <- the constructor arguments     (nfp.py:16-18)
+ *
+ * Conventions
+ *   - plain C types only; every buffer is caller-owned DEVICE memory (NCHW,
+ *     contiguous), the library keeps no pointer after a call returns and never
+ *     allocates on the hot path;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 on success, a negative NFPB200_E* code for argument
+ *     errors, a positive cudaError_t for CUDA failures.  No C++ exception
+ *     crosses the boundary.  nfpb200_status_string() renders either.
+ *   - re-entrant and thread-safe: no global mutable state besides one-time
+ *     cudaFuncSetAttribute calls.
+ *   - sm_100a only.  There is no CPU path in this library.
+ */
+#ifndef NFP_B200_H_
+#define NFP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFPB200_ABI_VERSION 1
+
+/* element type of x / y / gy / gx.  Accumulation is always fp32. */
+enum { NFPB200_F32 = 0, NFPB200_BF16 = 1 };
+
+/* torch.nn.Conv2d padding_mode (nfp.py:17, default 'reflect') */
+enum { NFPB200_PAD_ZEROS = 0, NFPB200_PAD_REFLECT = 1, NFPB200_PAD_REPLICATE = 2, NFPB200_PAD_CIRCULAR = 3 };
+
+/* the measures NFPPooling.__init__ accepts (nfp.py:85-118), lower-cased */
+enum {
+  NFPB200_NORM = 0,        /* nfp.py:141-148 */
+  NFPB200_COSINE = 1,      /* nfp.py:150-159  -- the only measure on the live model paths */
+  NFPB200_DOT = 2,         /* nfp.py:161-170 */
+  NFPB200_RMSE = 3,        /* nfp.py:172-179 */
+  NFPB200_GEMAN = 4,       /* nfp.py:181-193 */
+  NFPB200_ATTENTION = 5,   /* nfp.py:195-205 */
+  NFPB200_EMD = 6,         /* nfp.py:207-216 */
+  NFPB200_CANBERRA = 7,    /* nfp.py:218-227 */
+  NFPB200_HELLINGER = 8,   /* nfp.py:229-241 */
+  NFPB200_CHISQUARED1 = 9, /* nfp.py:243-252 */
+  NFPB200_CHISQUARED2 = 10,/* nfp.py:254-263 */
+  NFPB200_GFC = 11,        /* nfp.py:265-276 */
+  NFPB200_PEARSON = 12,    /* nfp.py:278-293 */
+  NFPB200_JEFFREY = 13,    /* nfp.py:295-308 */
+  NFPB200_SQUAREDCHORD = 14,/* nfp.py:310-324 */
+  NFPB200_SMITH = 15,      /* nfp.py:326-342 */
+  NFPB200_SCS = 16,        /* nfp.py:344-374 ('scs' / 'sharpened_cosine'), batch-coupled as in the reference */
+  NFPB200_NUM_MEASURES = 17
+};
+
+/* which implementation to use */
+enum {
+  NFPB200_PATH_AUTO = 0,    /* fused slab kernels when the problem qualifies, else the generic kernels */
+  NFPB200_PATH_GENERIC = 1, /* force the geometry-/measure-generic kernels */
+  NFPB200_PATH_FUSED = 2    /* force the fused kernels; NFPB200_EUNSUPPORTED when the problem does not qualify */
+};
+
+/* operations, for nfpb200_workspace_bytes / nfpb200_describe_path */
+enum { NFPB200_OP_FORWARD = 0, NFPB200_OP_BACKWARD = 1, NFPB200_OP_POOL_FORWARD = 2, NFPB200_OP_POOL_BACKWARD = 3 };
+
+/* error codes (negative); positive return values are cudaError_t */
+enum {
+  NFPB200_OK = 0,
+  NFPB200_EINVAL = -1,       /* null pointer / non-positive size / unknown enum */
+  NFPB200_EPADDING = -2,     /* reflect padding >= input dim, or circular padding > input dim (ATen's check) */
+  NFPB200_ESHAPE = -3,       /* kernel window larger than the padded input */
+  NFPB200_EWORKSPACE = -4,   /* workspace too small / null */
+  NFPB200_EUNSUPPORTED = -5, /* e.g. NFPB200_PATH_FUSED on a problem the fused kernels do not cover */
+  NFPB200_EDEVICE = -6       /* the current device is not sm_100 */
+};
+
+/* Constructor arguments of NFPPooling (nfp.py:16-18) plus the tensor shape. */
+typedef struct nfpb200_desc {
+  int32_t struct_bytes;     /* = sizeof(nfpb200_desc_t); ABI guard */
+  int32_t dtype;            /* NFPB200_F32 | NFPB200_BF16 */
+  int32_t B, C, H, W;       /* x is (B, C, H, W) contiguous */
+  int32_t R;                /* radius; kernel_size = 2R+1, out_channels K = (2R+1)^2 - 1 (nfp.py:38-39) */
+  int32_t stride;
+  int32_t padding;
+  int32_t dilation;
+  int32_t padding_mode;     /* NFPB200_PAD_* */
+  int32_t measure;          /* NFPB200_<MEASURE> */
+  int32_t similarity;       /* bool (nfp.py:29) */
+  int32_t difference_taps;  /* bool: neighbour taps emit centre - neighbour (nfp.py:74-76); only read by NORM / RMSE */
+  float eps;                /* nfp.py:33 */
+  float p;                  /* nfp.py:30: ord of NORM (INFINITY allowed), exponent of SCS */
+  float q_scs;              /* nfp.py:34 */
+  int32_t path;             /* NFPB200_PATH_* */
+} nfpb200_desc_t;
+
+int nfpb200_abi_version(void);
+
+/* Human-readable text for a status returned by any entry point (static storage). */
+const char* nfpb200_status_string(int status);
+
+/* (H', W') = Conv2d output size for the descriptor's geometry; validates the descriptor. */
+int nfpb200_output_shape(const nfpb200_desc_t* desc, int32_t* Ho, int32_t* Wo);
+
+/* Device scratch the given op needs (may be 0).  The caller allocates it and passes it in. */
+int nfpb200_workspace_bytes(const nfpb200_desc_t* desc, int32_t op, size_t* bytes);
+
+/* Writes the name of the kernel path the op would take ("fused/..." or "generic/...") into buf. */
+int nfpb200_describe_path(const nfpb200_desc_t* desc, int32_t op, char* buf, size_t buf_bytes);
+
+/* Number of kernel launches the op issues on `stream` (bench.py's gpu_launches). */
+int nfpb200_launch_count(const nfpb200_desc_t* desc, int32_t op, int32_t* launches);
+
+/* y (B, K, H', W') = NFP(x).  */
+int nfpb200_forward(const nfpb200_desc_t* desc, const void* x, void* y,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* gx (B, C, H, W) = d<gy, NFP(x)>/dx ; similarities are recomputed from x, nothing is saved by forward. */
+int nfpb200_backward(const nfpb200_desc_t* desc, const void* x, const void* gy, void* gx,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused head of nfp_pooling (NFP_Pooling.py:27-31): gap_x (B, C) = mean_hw x, gap_nfp (B, K) = mean_hw NFP(x).
+ * Both outputs are fp32 regardless of desc->dtype. */
+int nfpb200_pool_forward(const nfpb200_desc_t* desc, const void* x, float* gap_x, float* gap_nfp,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* gx = d(<g_gap_x, GAP(x)> + <g_gap_nfp, GAP(NFP(x))>)/dx ; g_* are fp32 (B, C) and (B, K). */
+int nfpb200_pool_backward(const nfpb200_desc_t* desc, const void* x, const float* g_gap_x,
+                          const float* g_gap_nfp, void* gx,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFP_B200_H_ */

@@ -1,0 +1,178 @@
+// extern "C" entry points of libnfp_b200.so -- see include/nfp_b200.h for the contract.
+// Validates the descriptor (same error conditions as the reference's Conv2d / reflection_pad2d
+// calls, models/pooling/nfp.py:42-58), picks the fused or the generic kernel path and launches.
+#include <stdio.h>
+#include <string.h>
+
+#include "nfp_common.cuh"
+
+using namespace nfp;
+
+namespace {
+
+int make_params(const nfpb200_desc_t* d, KParams* out) {
+  if (!d || d->struct_bytes != (int32_t)sizeof(nfpb200_desc_t)) return NFPB200_EINVAL;
+  if (d->dtype != NFPB200_F32 && d->dtype != NFPB200_BF16) return NFPB200_EINVAL;
+  if (d->B <= 0 || d->C <= 0 || d->H <= 0 || d->W <= 0) return NFPB200_EINVAL;
+  if (d->R < 1 || d->stride < 1 || d->dilation < 1 || d->padding < 0) return NFPB200_EINVAL;
+  if (d->padding_mode < NFPB200_PAD_ZEROS || d->padding_mode > NFPB200_PAD_CIRCULAR) return NFPB200_EINVAL;
+  if (d->measure < 0 || d->measure >= NFPB200_NUM_MEASURES) return NFPB200_EINVAL;
+  if (d->path < NFPB200_PATH_AUTO || d->path > NFPB200_PATH_FUSED) return NFPB200_EINVAL;
+  KParams P{};
+  P.B = d->B; P.C = d->C; P.H = d->H; P.W = d->W;
+  P.R = d->R; P.k = 2 * d->R + 1; P.K = P.k * P.k - 1;
+  P.stride = d->stride; P.pad = d->padding; P.dil = d->dilation; P.mode = d->padding_mode;
+  // ATen reflection_pad2d: "Padding size should be less than the corresponding input dimension";
+  // circular: "Padding value causes wrapping around more than once."
+  if (P.mode == NFPB200_PAD_REFLECT && P.pad > 0 && (P.pad >= P.H || P.pad >= P.W)) return NFPB200_EPADDING;
+  if (P.mode == NFPB200_PAD_CIRCULAR && (P.pad > P.H || P.pad > P.W)) return NFPB200_EPADDING;
+  const int span = P.dil * (P.k - 1) + 1;
+  if (P.H + 2 * P.pad < span || P.W + 2 * P.pad < span) return NFPB200_ESHAPE;
+  P.Ho = (P.H + 2 * P.pad - span) / P.stride + 1;
+  P.Wo = (P.W + 2 * P.pad - span) / P.stride + 1;
+  P.similarity = d->similarity != 0;
+  P.diff_taps = d->difference_taps != 0;
+  P.eps = d->eps; P.p = d->p; P.q = d->q_scs;
+  P.pkind = P_GENERAL;
+  if (d->measure == NFPB200_NORM) {
+    if (d->p == 1.f) P.pkind = P_ONE;
+    else if (d->p == 2.f) P.pkind = P_TWO;
+    else if (isinf(d->p) && d->p > 0) P.pkind = P_INF;
+    else if (d->p == 0.f) P.pkind = P_ZERO;
+    else if (!(d->p == d->p) || isinf(d->p)) return NFPB200_EINVAL;
+  }
+  *out = P;
+  return NFPB200_OK;
+}
+
+// 1 = fused, 0 = generic, <0 = error
+int choose_path(const nfpb200_desc_t* d, const KParams& P, int op) {
+  const bool can = fused_supported(P, d->dtype, d->measure, op);
+  if (d->path == NFPB200_PATH_FUSED) return can ? 1 : NFPB200_EUNSUPPORTED;
+  if (d->path == NFPB200_PATH_GENERIC) return 0;
+  return can ? 1 : 0;
+}
+
+int check_device() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return (int)e;
+  return major == 10 ? NFPB200_OK : NFPB200_EDEVICE;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nfpb200_abi_version(void) { return NFPB200_ABI_VERSION; }
+
+const char* nfpb200_status_string(int status) {
+  switch (status) {
+    case NFPB200_OK: return "ok";
+    case NFPB200_EINVAL: return "invalid argument (null pointer, bad size, unknown enum or descriptor size mismatch)";
+    case NFPB200_EPADDING:
+      return "Padding size should be less than the corresponding input dimension (reflect), or wraps more than "
+             "once (circular)";
+    case NFPB200_ESHAPE: return "Kernel size can't be greater than actual input size";
+    case NFPB200_EWORKSPACE: return "workspace missing or too small (see nfpb200_workspace_bytes)";
+    case NFPB200_EUNSUPPORTED: return "the fused kernels do not cover this problem (use NFPB200_PATH_AUTO)";
+    case NFPB200_EDEVICE: return "current CUDA device is not compute capability 10.x (B200, sm_100a)";
+    default: break;
+  }
+  if (status > 0) return cudaGetErrorString((cudaError_t)status);
+  return "unknown nfpb200 status";
+}
+
+int nfpb200_output_shape(const nfpb200_desc_t* desc, int32_t* Ho, int32_t* Wo) {
+  KParams P;
+  int rc = make_params(desc, &P);
+  if (rc) return rc;
+  if (!Ho || !Wo) return NFPB200_EINVAL;
+  *Ho = P.Ho;
+  *Wo = P.Wo;
+  return NFPB200_OK;
+}
+
+int nfpb200_workspace_bytes(const nfpb200_desc_t* desc, int32_t op, size_t* bytes) {
+  KParams P;
+  int rc = make_params(desc, &P);
+  if (rc) return rc;
+  if (!bytes || op < NFPB200_OP_FORWARD || op > NFPB200_OP_POOL_BACKWARD) return NFPB200_EINVAL;
+  int path = choose_path(desc, P, op);
+  if (path < 0) return path;
+  *bytes = path ? fused_workspace_bytes(P, desc->dtype, desc->measure, op)
+                : generic_workspace_bytes(P, desc->dtype, desc->measure, op);
+  return NFPB200_OK;
+}
+
+int nfpb200_describe_path(const nfpb200_desc_t* desc, int32_t op, char* buf, size_t buf_bytes) {
+  KParams P;
+  int rc = make_params(desc, &P);
+  if (rc) return rc;
+  if (!buf || buf_bytes == 0 || op < NFPB200_OP_FORWARD || op > NFPB200_OP_POOL_BACKWARD) return NFPB200_EINVAL;
+  int path = choose_path(desc, P, op);
+  if (path < 0) return path;
+  snprintf(buf, buf_bytes, "%s", path ? fused_name(P, desc->dtype, desc->measure, op) : "generic/pairs");
+  return NFPB200_OK;
+}
+
+int nfpb200_launch_count(const nfpb200_desc_t* desc, int32_t op, int32_t* launches) {
+  KParams P;
+  int rc = make_params(desc, &P);
+  if (rc) return rc;
+  if (!launches || op < NFPB200_OP_FORWARD || op > NFPB200_OP_POOL_BACKWARD) return NFPB200_EINVAL;
+  int path = choose_path(desc, P, op);
+  if (path < 0) return path;
+  *launches = path ? fused_launch_count(P, desc->dtype, desc->measure, op)
+                   : generic_launch_count(P, desc->dtype, desc->measure, op);
+  return NFPB200_OK;
+}
+
+#define NFP_PROLOGUE(OP)                                                                      \
+  KParams P;                                                                                  \
+  int rc = make_params(desc, &P);                                                             \
+  if (rc) return rc;                                                                          \
+  rc = check_device();                                                                        \
+  if (rc) return rc;                                                                          \
+  const int path = choose_path(desc, P, OP);                                                  \
+  if (path < 0) return path;                                                                  \
+  const size_t need = path ? fused_workspace_bytes(P, desc->dtype, desc->measure, OP)         \
+                           : generic_workspace_bytes(P, desc->dtype, desc->measure, OP);      \
+  if (need > 0 && (!workspace || workspace_bytes < need)) return NFPB200_EWORKSPACE;          \
+  LaunchCtx ctx{(cudaStream_t)stream, workspace, workspace_bytes};
+
+int nfpb200_forward(const nfpb200_desc_t* desc, const void* x, void* y, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  if (!x || !y) return NFPB200_EINVAL;
+  NFP_PROLOGUE(NFPB200_OP_FORWARD)
+  return path ? fused_forward(P, desc->dtype, x, y, ctx) : generic_forward(P, desc->dtype, desc->measure, x, y, ctx);
+}
+
+int nfpb200_backward(const nfpb200_desc_t* desc, const void* x, const void* gy, void* gx, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  if (!x || !gy || !gx) return NFPB200_EINVAL;
+  NFP_PROLOGUE(NFPB200_OP_BACKWARD)
+  return path ? fused_backward(P, desc->dtype, x, gy, gx, ctx)
+              : generic_backward(P, desc->dtype, desc->measure, x, gy, gx, ctx);
+}
+
+int nfpb200_pool_forward(const nfpb200_desc_t* desc, const void* x, float* gap_x, float* gap_nfp, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (!x || !gap_x || !gap_nfp) return NFPB200_EINVAL;
+  NFP_PROLOGUE(NFPB200_OP_POOL_FORWARD)
+  return path ? fused_pool_forward(P, desc->dtype, x, gap_x, gap_nfp, ctx)
+              : generic_pool_forward(P, desc->dtype, desc->measure, x, gap_x, gap_nfp, ctx);
+}
+
+int nfpb200_pool_backward(const nfpb200_desc_t* desc, const void* x, const float* g_gap_x, const float* g_gap_nfp,
+                          void* gx, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !g_gap_x || !g_gap_nfp || !gx) return NFPB200_EINVAL;
+  NFP_PROLOGUE(NFPB200_OP_POOL_BACKWARD)
+  return path ? fused_pool_backward(P, desc->dtype, x, g_gap_x, g_gap_nfp, gx, ctx)
+              : generic_pool_backward(P, desc->dtype, desc->measure, x, g_gap_x, g_gap_nfp, gx, ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+// Shared definitions for the NFP kernels (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "nfp_b200.h"
+
+namespace nfp {
+
+// how `p` of the NORM measure is evaluated (torch.linalg.norm ord semantics, nfp.py:145)
+enum { P_GENERAL = 0, P_ONE = 1, P_TWO = 2, P_INF = 3, P_ZERO = 4 };
+
+// Kernel-side view of nfpb200_desc_t (validated, with derived sizes).
+struct KParams {
+  int B, C, H, W;
+  int R, k, K;          // k = 2R+1, K = k*k-1 (nfp.py:38-39)
+  int stride, pad, dil, mode;
+  int Ho, Wo;
+  int similarity, diff_taps, pkind;
+  float eps, p, q;
+};
+
+// Source index of padded coordinate i (already shifted by -pad); -1 = implicit zero.
+// Same rule as F.pad / Conv2d(padding_mode=...) which the reference relies on (nfp.py:42-58).
+__host__ __device__ __forceinline__ int map_index(int i, int n, int mode) {
+  if (i >= 0 && i < n) return i;
+  switch (mode) {
+    case NFPB200_PAD_REFLECT:   return i < 0 ? -i : 2 * (n - 1) - i;
+    case NFPB200_PAD_REPLICATE: return i < 0 ? 0 : n - 1;
+    case NFPB200_PAD_CIRCULAR:  return i < 0 ? i + n : i - n;
+    default:                    return -1;
+  }
+}
+
+// tap index t in [0,K) -> (row a, col b) of the k x k window, centre removed, row-major (nfp.py:64-67)
+__host__ __device__ __forceinline__ void tap_rc(int t, int k, int K, int& a, int& b) {
+  int tt = t < (K >> 1) ? t : t + 1;
+  a = tt / k;
+  b = tt - a * k;
+}
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float sgnf(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
+
+// ---- host-side launch plumbing ------------------------------------------------------------
+
+struct LaunchCtx {
+  cudaStream_t stream;
+  void* ws;
+  size_t ws_bytes;
+};
+
+// generic (any geometry, any measure) kernels: nfp_generic.cu
+size_t generic_workspace_bytes(const KParams& P, int dtype, int measure, int op);
+int generic_launch_count(const KParams& P, int dtype, int measure, int op);
+int generic_forward(const KParams& P, int dtype, int measure, const void* x, void* y, const LaunchCtx& ctx);
+int generic_backward(const KParams& P, int dtype, int measure, const void* x, const void* gy, void* gx,
+                     const LaunchCtx& ctx);
+int generic_pool_forward(const KParams& P, int dtype, int measure, const void* x, float* gap_x, float* gap_nfp,
+                         const LaunchCtx& ctx);
+int generic_pool_backward(const KParams& P, int dtype, int measure, const void* x, const float* g_gap_x,
+                          const float* g_gap_nfp, void* gx, const LaunchCtx& ctx);
+
+// fused slab kernels (cosine, stride 1, dilation 1, pad = R): nfp_fused.cu
+bool fused_supported(const KParams& P, int dtype, int measure, int op);
+const char* fused_name(const KParams& P, int dtype, int measure, int op);
+size_t fused_workspace_bytes(const KParams& P, int dtype, int measure, int op);
+int fused_launch_count(const KParams& P, int dtype, int measure, int op);
+int fused_forward(const KParams& P, int dtype, const void* x, void* y, const LaunchCtx& ctx);
+int fused_backward(const KParams& P, int dtype, const void* x, const void* gy, void* gx, const LaunchCtx& ctx);
+int fused_pool_forward(const KParams& P, int dtype, const void* x, float* gap_x, float* gap_nfp,
+                       const LaunchCtx& ctx);
+int fused_pool_backward(const KParams& P, int dtype, const void* x, const float* g_gap_x, const float* g_gap_nfp,
+                        void* gx, const LaunchCtx& ctx);
+
+}  // namespace nfp

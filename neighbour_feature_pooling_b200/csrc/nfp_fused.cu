@@ -1,0 +1,649 @@
+// Fused NFP slab kernels for sm_100a: cosine measure, stride 1, dilation 1, padding = R
+// (the configuration every live model path of the reference uses: models/NFP_Pooling.py:10-16,
+// models/texture_pooling.py:232,302).
+//
+// One work item = (image b, channel slice s of S).  The S CTAs of an image form a thread-block
+// cluster.  Each CTA
+//   1. stages its C/S x H x W slice of x into shared memory with ONE TMA bulk copy
+//      (cp.async.bulk + mbarrier; bf16 inputs are widened to fp32 while staging),
+//   2. pass A: accumulates, per pixel p, ||x_p||^2 and the dot products with the (k*k-1)/2
+//      "forward" window neighbours (dot(p,q) == dot(q,p), so half the window suffices), each
+//      thread owning a TW-pixel row strip and looping over channels with the strip's
+//      accumulators in registers,
+//   3. reduces the per-pixel table over warps (shared memory) and over the cluster (DSMEM),
+//   4. forward: writes y = dot / (max(|p|,eps) max(|q|,eps)) for the K taps -- nothing else
+//      ever touches HBM; pooled mode reduces y and x over the plane instead,
+//   5. backward: turns gy and the table into a per-pixel k x k stencil of coefficients
+//      Wd[p][o] (closed form of ATen's cosine_similarity backward) and
+//      pass B: gx[c][p] = sum_o Wd[p][o] * x[c][p+o] from the slab that is still resident,
+//      staged per warp through shared memory so that global stores are 16-byte, fully coalesced.
+// The (B, C*(k*k-1), H, W) neighbour tensor of the reference (nfp.py:153-154) never exists.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
+#include "nfp_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace nfp {
+namespace {
+
+enum { MODE_FWD = 0, MODE_BWD = 1, MODE_POOL_FWD = 2, MODE_POOL_BWD = 3 };
+
+struct FusedArgs {
+  const void* x;
+  const void* gy;
+  void* y;
+  void* gx;
+  const float* g_gap_x;
+  const float* g_gap_nfp;
+  float* gap_x;
+  float* gap_nfp;
+  int B, C, Cs, S;
+  int mode, pad_mode, similarity;
+  float eps;
+};
+
+template <int H_, int W_, int R_, int TW_>
+struct Cfg {
+  static constexpr int H = H_, W = W_, R = R_, TW = TW_;
+  static constexpr int k = 2 * R + 1, KK = k * k, K = KK - 1, CTR = R * k + R;
+  static constexpr int P = H * W;
+  static constexpr int NSX = W / TW;        // strips per row
+  static constexpr int NS = H * NSX;        // strips per channel plane
+  static constexpr int ND = K / 2;          // forward directions
+  static constexpr int NV = ND + 1;         // table entries per pixel: |x|^2 + ND dots
+  static constexpr int CPW = 32 / NS;       // channels per warp iteration
+  static constexpr int LANES = CPW * NS;    // active lanes
+  static constexpr int XW = (NSX == 1) ? TW : TW + 2 * R;  // loaded columns per row (halo only if strips abut)
+  static constexpr int XOFF = (NSX == 1) ? 0 : R;          // column index of strip pixel 0 inside a loaded row
+  static_assert(W % TW == 0, "strip width must divide W");
+  static_assert(NS <= 32 && CPW >= 1 && (CPW & (CPW - 1)) == 0, "channels per warp must be a power of two");
+};
+
+// ---- PTX helpers: mbarrier + TMA bulk copy -----------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+// dot(x_p, x_q) from the symmetric table; (dy, dx) = q - p, both within the window
+template <class C>
+__device__ __forceinline__ float table_dot(const float* tab, int p, int q, int dy, int dx) {
+  int o = (dy + C::R) * C::k + dx + C::R;
+  if (o == C::CTR) return tab[p * C::NV];
+  return o > C::CTR ? tab[p * C::NV + (o - C::CTR)] : tab[q * C::NV + (C::CTR - o)];
+}
+
+template <class C>
+struct Smem {
+  // offsets in floats from the start of dynamic shared memory (slab first: 128-byte aligned).
+  // The per-warp tables (pass A), the coefficient scratch (backward) and the y tile (pooled
+  // forward) are never live at the same time and share one region.
+  int slab, tloc, tfull, wtab, gy, wd, inv, rn, selfw, stg, ytab, mbar, total;
+  __host__ __device__ Smem(int Cs, int NW) {
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+    slab = take(Cs * C::P);
+    tloc = take(C::P * C::NV);
+    tfull = take(C::P * C::NV);
+    mbar = take(4);
+    const int u0 = o;
+    wtab = take(NW * C::P * C::NV);
+    const int u1 = o;
+    o = u0;
+    gy = take(C::K * C::P);
+    wd = take(C::P * C::KK);
+    inv = take(C::P);
+    rn = take(C::P);
+    selfw = take(C::P);
+    stg = take(NW * C::LANES * C::TW);
+    const int u2 = o;
+    o = u0;
+    ytab = take(C::K * C::P);
+    const int u3 = o;
+    total = u1 > u2 ? (u1 > u3 ? u1 : u3) : (u2 > u3 ? u2 : u3);
+  }
+};
+
+template <typename T, class C, int NW>
+__global__ void __launch_bounds__(NW * 32, 4) fused_kernel(FusedArgs a) {
+  constexpr int H = C::H, W = C::W, R = C::R, TW = C::TW, k = C::k, KK = C::KK, K = C::K, P = C::P;
+  constexpr int NV = C::NV, NS = C::NS, NSX = C::NSX, CPW = C::CPW, LANES = C::LANES, XW = C::XW, XOFF = C::XOFF;
+  constexpr int NT = NW * 32;
+  extern __shared__ __align__(128) float smem[];
+  const Smem<C> L(a.Cs, NW);
+  float* slab = smem + L.slab;
+  float* tloc = smem + L.tloc;
+  float* tfull = smem + L.tfull;
+  float* wtab = smem + L.wtab;
+  float* gyS = smem + L.gy;
+  float* Wd = smem + L.wd;
+  float* inv = smem + L.inv;
+  float* rn = smem + L.rn;
+  float* selfw = smem + L.selfw;
+  float* stg = smem + L.stg;
+  float* ytab = smem + L.ytab;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + L.mbar);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = a.S, Cs = a.Cs;
+  const int b = blockIdx.x / S, rank = blockIdx.x % S;
+  const int ch_base = rank * Cs;
+  const size_t img_off = ((size_t)b * a.C + ch_base) * P;
+  const bool bwd = (a.mode == MODE_BWD || a.mode == MODE_POOL_BWD);
+  const bool pooled = (a.mode == MODE_POOL_FWD || a.mode == MODE_POOL_BWD);
+  const float sgn = a.similarity ? 1.f : -1.f;
+
+  // ---- 1. stage the slab ------------------------------------------------------------------------
+  if constexpr (sizeof(T) == 4) {
+    if (tid == 0) {
+      mbar_init(mbar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)(Cs * P * 4);
+      mbar_expect_tx(mbar, bytes);
+      const char* src = reinterpret_cast<const char*>((const float*)a.x + img_off);
+      char* dst = reinterpret_cast<char*>(slab);
+      for (uint32_t off = 0; off < bytes; off += 65536u) {
+        uint32_t n = bytes - off < 65536u ? bytes - off : 65536u;
+        bulk_g2s(dst + off, src + off, n, mbar);
+      }
+    }
+  } else {
+    const uint4* src = reinterpret_cast<const uint4*>((const __nv_bfloat16*)a.x + img_off);
+    const int n16 = Cs * P / 8;
+#pragma unroll 4
+    for (int i = tid; i < n16; i += NT) {
+      uint4 v = __ldg(src + i);
+      float4 lo, hi;
+      lo.x = __uint_as_float(v.x << 16); lo.y = __uint_as_float(v.x & 0xffff0000u);
+      lo.z = __uint_as_float(v.y << 16); lo.w = __uint_as_float(v.y & 0xffff0000u);
+      hi.x = __uint_as_float(v.z << 16); hi.y = __uint_as_float(v.z & 0xffff0000u);
+      hi.z = __uint_as_float(v.w << 16); hi.w = __uint_as_float(v.w & 0xffff0000u);
+      reinterpret_cast<float4*>(slab)[2 * i] = lo;
+      reinterpret_cast<float4*>(slab)[2 * i + 1] = hi;
+    }
+  }
+
+  // per-thread strip geometry (independent of the channel)
+  const bool lane_on = lane < LANES;
+  const int chslot = lane_on ? lane / NS : 0;
+  const int pos = lane_on ? lane % NS : 0;
+  const int r = pos / NSX, c0 = (pos % NSX) * TW;
+  const int strip_off = r * W + c0;
+  // column offsets (relative to c0) of the loaded row window, clamped into the map
+  int coff[XW];
+#pragma unroll
+  for (int jj = 0; jj < XW; ++jj) {
+    int c = c0 + jj - XOFF;
+    c = c < 0 ? 0 : (c > W - 1 ? W - 1 : c);
+    coff[jj] = c - c0;
+  }
+  const int n_iter = (Cs + NW * CPW - 1) / (NW * CPW);
+
+  if constexpr (sizeof(T) == 4) {
+    mbar_wait(mbar, 0);
+  } else {
+    __syncthreads();
+  }
+
+  // ---- pooled forward: GAP(x) for this CTA's channels (NFP_Pooling.py:27) ------------------------
+  if (a.mode == MODE_POOL_FWD) {
+    for (int ch = tid; ch < Cs; ch += NT) {
+      const float* pl = slab + ch * P;
+      float s = 0.f;
+#pragma unroll 7
+      for (int e = 0; e < P; ++e) s += pl[e];
+      a.gap_x[(size_t)b * a.C + ch_base + ch] = s / (float)P;
+    }
+  }
+
+  // ---- 2. pass A: per-pixel |x|^2 and forward-direction dots --------------------------------------
+  {
+    float acc[TW][NV];
+#pragma unroll
+    for (int j = 0; j < TW; ++j)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[j][v] = 0.f;
+    int roff[R + 1];
+#pragma unroll
+    for (int dy = 0; dy <= R; ++dy) roff[dy] = ((r + dy > H - 1 ? H - 1 : r + dy) - r) * W;
+
+    for (int it = 0; it < n_iter; ++it) {
+      const int ch = (it * NW + warp) * CPW + chslot;
+      if (lane_on && ch < Cs) {
+        const float* base = slab + ch * P + strip_off;
+        float xr[R + 1][XW];
+#pragma unroll
+        for (int dy = 0; dy <= R; ++dy)
+#pragma unroll
+          for (int jj = 0; jj < XW; ++jj) xr[dy][jj] = base[roff[dy] + coff[jj]];
+#pragma unroll
+        for (int j = 0; j < TW; ++j) {
+          const float c = xr[0][j + XOFF];
+          acc[j][0] = fmaf(c, c, acc[j][0]);
+#pragma unroll
+          for (int dx = 1; dx <= R; ++dx) {
+            if (j + dx + XOFF < XW) acc[j][dx] = fmaf(c, xr[0][j + dx + XOFF], acc[j][dx]);
+          }
+#pragma unroll
+          for (int dy = 1; dy <= R; ++dy)
+#pragma unroll
+            for (int dx = -R; dx <= R; ++dx) {
+              if (j + dx + XOFF >= 0 && j + dx + XOFF < XW)
+                acc[j][dy * k + dx] = fmaf(c, xr[dy][j + dx + XOFF], acc[j][dy * k + dx]);
+            }
+        }
+      }
+    }
+    // reduce over the channel slots inside the warp, then publish one table per warp
+#pragma unroll
+    for (int j = 0; j < TW; ++j)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float s = acc[j][v];
+#pragma unroll
+        for (int d = CPW / 2; d >= 1; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d * NS);
+        if (lane < NS) wtab[warp * (P * NV) + (pos * TW + j) * NV + v] = s;
+      }
+  }
+  __syncthreads();
+  for (int i = tid; i < P * NV; i += NT) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += wtab[w * (P * NV) + i];
+    tloc[i] = s;
+  }
+  // ---- 3. cluster reduction over the channel slices (DSMEM) ---------------------------------------
+  if (S > 1) {
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    for (int i = tid; i < P * NV; i += NT) {
+      float s = 0.f;
+      for (int rk = 0; rk < S; ++rk) s += cluster.map_shared_rank(tloc, rk)[i];
+      tfull[i] = s;
+    }
+    cluster.sync();  // peers are done reading tloc; also orders tfull for the whole CTA
+  } else {
+    __syncthreads();
+    tfull = tloc;
+  }
+
+  auto row_of = [&](int p) { return p / W; };
+  auto col_of = [&](int p) { return p - (p / W) * W; };
+
+  // ---- 4. forward value -----------------------------------------------------------------------------
+  if (!bwd) {
+    // the K*P outputs of the image are split across the cluster ranks
+    const int per = (K * P + S - 1) / S;
+    const int lo = rank * per, hi = (lo + per < K * P) ? lo + per : K * P;
+    for (int idx = lo + tid; idx < hi; idx += NT) {
+      const int n = idx / P, p = idx - n * P;
+      int ta, tb;
+      tap_rc(n, k, K, ta, tb);
+      const int pr = row_of(p), pc = col_of(p);
+      const int qr = map_index(pr + ta - R, H, a.pad_mode), qc = map_index(pc + tb - R, W, a.pad_mode);
+      float yv = 0.f;
+      if (qr >= 0 && qc >= 0) {
+        const int q = qr * W + qc;
+        const float d = table_dot<C>(tfull, p, q, qr - pr, qc - pc);
+        const float Np = fmaxf(sqrtf(tfull[p * NV]), a.eps), Nq = fmaxf(sqrtf(tfull[q * NV]), a.eps);
+        yv = d / (Np * Nq);
+      }
+      if (!a.similarity) yv = 1.f - yv;
+      if (pooled) {
+        ytab[idx] = yv;
+      } else {
+        reinterpret_cast<T*>(a.y)[(size_t)b * K * P + idx] = from_f32<T>(yv);
+      }
+    }
+    if (pooled) {
+      // GAP over the plane of every tap (NFP_Pooling.py:31); rank r reduced its own index range
+      if (S > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        cluster.sync();
+        if (rank == 0) {
+          for (int n = warp; n < K; n += NW) {
+            float s = 0.f;
+            for (int p = lane; p < P; p += 32) {
+              const int idx = n * P + p;
+              s += cluster.map_shared_rank(ytab, idx / per)[idx];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) a.gap_nfp[(size_t)b * K + n] = s / (float)P;
+          }
+        }
+        cluster.sync();
+      } else {
+        __syncthreads();
+        for (int n = warp; n < K; n += NW) {
+          float s = 0.f;
+          for (int p = lane; p < P; p += 32) s += ytab[n * P + p];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (lane == 0) a.gap_nfp[(size_t)b * K + n] = s / (float)P;
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- 5. backward: stencil coefficients ------------------------------------------------------------
+  for (int p = tid; p < P; p += NT) {
+    const float nsq = tfull[p * NV];
+    const float nrm = sqrtf(nsq), N = fmaxf(nrm, a.eps);
+    inv[p] = 1.f / N;
+    rn[p] = nrm > 0.f ? 1.f / (N * nrm) : 0.f;
+    selfw[p] = 0.f;
+  }
+  if (pooled) {
+    for (int idx = tid; idx < K * P; idx += NT)
+      gyS[idx] = sgn * a.g_gap_nfp[(size_t)b * K + idx / P] * (1.f / (float)P);
+  } else {
+    const T* g = reinterpret_cast<const T*>(a.gy) + (size_t)b * K * P;
+    for (int idx = tid; idx < K * P; idx += NT) gyS[idx] = sgn * to_f32(g[idx]);
+  }
+  __syncthreads();
+  // direct (in-map) pairs: Wd[p][o] = (G[n_o][p] + G[~n_o][q]) / (N_p N_q), q = p + off(o)
+  for (int idx = tid; idx < P * KK; idx += NT) {
+    const int p = idx / KK, o = idx - p * KK;
+    float wv = 0.f;
+    if (o != C::CTR) {
+      const int dy = o / k - R, dx = o % k - R;
+      const int qr = row_of(p) + dy, qc = col_of(p) + dx;
+      if (qr >= 0 && qr < H && qc >= 0 && qc < W) {
+        const int q = qr * W + qc;
+        const int n = o < C::CTR ? o : o - 1;
+        wv = (gyS[n * P + p] + gyS[(K - 1 - n) * P + q]) * inv[p] * inv[q];
+      }
+    }
+    Wd[idx] = wv;
+  }
+  __syncthreads();
+  // padded taps: the neighbour is a reflected / replicated in-map pixel v
+  if (a.pad_mode != NFPB200_PAD_ZEROS) {
+    for (int idx = tid; idx < K * P; idx += NT) {
+      const int n = idx / P, p = idx - n * P;
+      int ta, tb;
+      tap_rc(n, k, K, ta, tb);
+      const int pr = row_of(p), pc = col_of(p);
+      const int rr = pr + ta - R, cc = pc + tb - R;
+      if (rr >= 0 && rr < H && cc >= 0 && cc < W) continue;
+      const int vr = map_index(rr, H, a.pad_mode), vc = map_index(cc, W, a.pad_mode);
+      const int v = vr * W + vc;
+      const float wv = gyS[idx] * inv[p] * inv[v];
+      if (v == p) {
+        atomicAdd(&selfw[p], 2.f * wv);
+      } else {
+        atomicAdd(&Wd[p * KK + (vr - pr + R) * k + (vc - pc + R)], wv);
+        atomicAdd(&Wd[v * KK + (pr - vr + R) * k + (pc - vc + R)], wv);
+      }
+    }
+    __syncthreads();
+  }
+  // centre tap: -(1/(N_p |x_p|)) * sum_o Wd[p][o] dot(p, q_o)   (+ the self pairs)
+  for (int p = tid; p < P; p += NT) {
+    float s = 0.f;
+    const int pr = row_of(p), pc = col_of(p);
+#pragma unroll
+    for (int o = 0; o < KK; ++o) {
+      if (o == C::CTR) continue;
+      const int dy = o / k - R, dx = o % k - R;
+      const int qr = pr + dy, qc = pc + dx;
+      if (qr >= 0 && qr < H && qc >= 0 && qc < W)
+        s = fmaf(Wd[p * KK + o], table_dot<C>(tfull, p, qr * W + qc, dy, dx), s);
+    }
+    const float sw = selfw[p];
+    Wd[p * KK + C::CTR] = sw - rn[p] * (s + sw * tfull[p * NV]);
+  }
+  __syncthreads();
+
+  // ---- pass B: gx = stencil(x) from the resident slab ---------------------------------------------
+  {
+    float wr[TW][KK];
+#pragma unroll
+    for (int j = 0; j < TW; ++j)
+#pragma unroll
+      for (int o = 0; o < KK; ++o) wr[j][o] = Wd[(pos * TW + j) * KK + o];
+    int roff[k];
+#pragma unroll
+    for (int dy = -R; dy <= R; ++dy) {
+      int rr = r + dy;
+      rr = rr < 0 ? 0 : (rr > H - 1 ? H - 1 : rr);
+      roff[dy + R] = (rr - r) * W;
+    }
+    float* mystg = stg + warp * (LANES * TW);
+    const float invP = 1.f / (float)P;
+    T* gxg = reinterpret_cast<T*>(a.gx) + img_off;
+    for (int it = 0; it < n_iter; ++it) {
+      const int ch_w = (it * NW + warp) * CPW;  // first channel of this warp's group (warp-uniform)
+      if (ch_w >= Cs) break;
+      const int ch = ch_w + chslot;
+      if (lane_on) {
+        const float* base = slab + ch * P + strip_off;
+        float out[TW];
+        const float g0 = a.mode == MODE_POOL_BWD ? a.g_gap_x[(size_t)b * a.C + ch_base + ch] * invP : 0.f;
+#pragma unroll
+        for (int j = 0; j < TW; ++j) out[j] = g0;
+#pragma unroll
+        for (int dy = -R; dy <= R; ++dy) {
+          float xr[XW];
+#pragma unroll
+          for (int jj = 0; jj < XW; ++jj) xr[jj] = base[roff[dy + R] + coff[jj]];
+#pragma unroll
+          for (int j = 0; j < TW; ++j)
+#pragma unroll
+            for (int dx = -R; dx <= R; ++dx) {
+              if (j + dx + XOFF >= 0 && j + dx + XOFF < XW)
+                out[j] = fmaf(wr[j][(dy + R) * k + dx + R], xr[j + dx + XOFF], out[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < TW; ++j) mystg[lane * TW + j] = out[j];
+      }
+      __syncwarp();
+      // the warp's LANES*TW outputs are contiguous in gx: channels [ch_w, ch_w + CPW)
+      constexpr int NOUT = LANES * TW;
+      T* dst = gxg + (size_t)ch_w * P;
+      if constexpr (sizeof(T) == 4) {
+        static_assert(NOUT % 4 == 0, "");
+        for (int i = lane; i < NOUT / 4; i += 32)
+          reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(mystg)[i];
+      } else {
+        static_assert(NOUT % 4 == 0, "");
+        for (int i = lane; i < NOUT / 4; i += 32) {
+          const float4 v = reinterpret_cast<const float4*>(mystg)[i];
+          __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          reinterpret_cast<uint2*>(dst)[i] = pk;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+constexpr int kNW = 4;
+
+// ---- host side --------------------------------------------------------------------------------------
+
+struct Plan {
+  bool ok;
+  int S;          // cluster size (channel slices per image)
+  int Cs;
+  size_t smem;
+  const char* name;
+};
+
+int forced_split() {
+  // NFPB200_FUSED_SPLIT=<1|2|4|8> pins the cluster size (tuning / tests); default: heuristic below
+  static const int v = [] {
+    const char* e = getenv("NFPB200_FUSED_SPLIT");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
+template <class C>
+Plan plan_for(const KParams& P, int dtype) {
+  const int esz = dtype == NFPB200_BF16 ? 2 : 4;
+  Plan best{false, 1, 0, 0, ""};
+  int best_tier = 99;
+  for (int S = 1; S <= 8; S *= 2) {
+    if (P.C % S) break;
+    if (forced_split() && S != forced_split()) continue;
+    const int Cs = P.C / S;
+    if (Cs % C::CPW) continue;
+    if (((size_t)Cs * C::P * esz) % 16) continue;                       // TMA bulk copy granularity
+    if (((size_t)C::CPW * C::P * esz) % (esz == 4 ? 16 : 8)) continue;  // vector stores of pass B
+    Smem<C> L(Cs, kNW);
+    const size_t bytes = (size_t)L.total * 4;
+    // smallest split that leaves room for 3 CTAs per SM, else for 2, else anything that fits
+    const int tier = bytes <= 75 * 1024 ? 0 : (bytes <= 113 * 1024 ? 1 : (bytes <= 227 * 1024 ? 2 : 99));
+    if (tier < best_tier) {
+      best_tier = tier;
+      best = Plan{true, S, Cs, bytes, ""};
+    }
+  }
+  return best;
+}
+
+template <typename T, class C>
+int launch_t(const KParams& P, const FusedArgs& a0, const Plan& pl, cudaStream_t stream) {
+  FusedArgs a = a0;
+  a.S = pl.S;
+  a.Cs = pl.Cs;
+  auto kern = fused_kernel<T, C, kNW>;
+  // once per instantiation (one process drives one GPU): allow the full 227 KB of dynamic smem
+  static const cudaError_t attr_rc =
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (attr_rc != cudaSuccess) return (int)attr_rc;
+  cudaError_t e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(P.B * pl.S));
+  cfg.blockDim = dim3(kNW * 32);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)pl.S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pl.S > 1 ? 1 : 0;
+  e = cudaLaunchKernelEx(&cfg, kern, a);
+  return (int)e;
+}
+
+// the (H, W, R) shapes with a fused instantiation
+#define NFP_FUSED_SHAPES(X) \
+  X(7, 7, 1, 7)             \
+  X(14, 14, 1, 7)           \
+  X(2, 2, 1, 2)             \
+  X(4, 4, 1, 4)
+
+template <typename F>
+bool for_shape(const KParams& P, F&& f) {
+#define X(H_, W_, R_, TW_) \
+  if (P.H == H_ && P.W == W_ && P.R == R_) { f(Cfg<H_, W_, R_, TW_>{}); return true; }
+  NFP_FUSED_SHAPES(X)
+#undef X
+  return false;
+}
+
+bool geometry_ok(const KParams& P, int measure) {
+  return measure == NFPB200_COSINE && P.stride == 1 && P.dil == 1 && P.pad == P.R &&
+         P.mode != NFPB200_PAD_CIRCULAR;
+}
+
+int run(const KParams& P, int dtype, FusedArgs a, cudaStream_t stream) {
+  a.B = P.B; a.C = P.C;
+  a.pad_mode = P.mode; a.similarity = P.similarity; a.eps = P.eps;
+  int rc = NFPB200_EUNSUPPORTED;
+  for_shape(P, [&](auto cfg) {
+    using C = decltype(cfg);
+    Plan pl = plan_for<C>(P, dtype);
+    if (!pl.ok) return;
+    rc = dtype == NFPB200_BF16 ? launch_t<__nv_bfloat16, C>(P, a, pl, stream) : launch_t<float, C>(P, a, pl, stream);
+  });
+  return rc;
+}
+
+}  // namespace
+
+bool fused_supported(const KParams& P, int dtype, int measure, int op) {
+  (void)op;
+  if (!geometry_ok(P, measure)) return false;
+  bool ok = false;
+  for_shape(P, [&](auto cfg) { ok = plan_for<decltype(cfg)>(P, dtype).ok; });
+  return ok;
+}
+
+const char* fused_name(const KParams& P, int dtype, int measure, int op) {
+  (void)dtype; (void)measure; (void)op;
+  const char* nm = "fused/slab";
+#define X(H_, W_, R_, TW_) \
+  if (P.H == H_ && P.W == W_ && P.R == R_) nm = "fused/slab_" #H_ "x" #W_ "_r" #R_;
+  NFP_FUSED_SHAPES(X)
+#undef X
+  return nm;
+}
+
+size_t fused_workspace_bytes(const KParams&, int, int, int) { return 0; }
+int fused_launch_count(const KParams&, int, int, int) { return 1; }
+
+int fused_forward(const KParams& P, int dtype, const void* x, void* y, const LaunchCtx& ctx) {
+  FusedArgs a{};
+  a.x = x; a.y = y; a.mode = MODE_FWD;
+  return run(P, dtype, a, ctx.stream);
+}
+int fused_backward(const KParams& P, int dtype, const void* x, const void* gy, void* gx, const LaunchCtx& ctx) {
+  FusedArgs a{};
+  a.x = x; a.gy = gy; a.gx = gx; a.mode = MODE_BWD;
+  return run(P, dtype, a, ctx.stream);
+}
+int fused_pool_forward(const KParams& P, int dtype, const void* x, float* gap_x, float* gap_nfp,
+                       const LaunchCtx& ctx) {
+  FusedArgs a{};
+  a.x = x; a.gap_x = gap_x; a.gap_nfp = gap_nfp; a.mode = MODE_POOL_FWD;
+  return run(P, dtype, a, ctx.stream);
+}
+int fused_pool_backward(const KParams& P, int dtype, const void* x, const float* g_gap_x, const float* g_gap_nfp,
+                        void* gx, const LaunchCtx& ctx) {
+  FusedArgs a{};
+  a.x = x; a.g_gap_x = g_gap_x; a.g_gap_nfp = g_gap_nfp; a.gx = gx; a.mode = MODE_POOL_BWD;
+  return run(P, dtype, a, ctx.stream);
+}
+
+}  // namespace nfp

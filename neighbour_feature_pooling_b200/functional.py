@@ -1,0 +1,233 @@
+"""Autograd bindings of the NFP C ABI.
+
+``nfp_similarity``  -- the operator behind ``NFPPooling.forward``
+                       (reference models/pooling/nfp.py:132-134): (B,C,H,W) -> (B,K,H',W')
+``nfp_gap_pair``    -- the fused head of ``nfp_pooling.forward``
+                       (reference models/NFP_Pooling.py:27-31): (GAP(x), GAP(NFP(x)))
+
+Both launch the hand-written sm_100a kernels of libnfp_b200.so on the current
+CUDA stream.  Backward recomputes the similarities from ``x``; nothing but ``x``
+is saved.  There is no CPU or PyTorch implementation behind these functions:
+CPU tensors are rejected (except the constructor-time shape probes described in
+``shape_probe``).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass, replace
+
+import torch
+
+from . import _capi
+
+
+@dataclass(frozen=True)
+class NFPConfig:
+    """Constructor arguments of the reference NFPPooling (nfp.py:16-18) that shape the math."""
+    R: int = 1
+    measure: str = "norm"          # lower-cased spelling, nfp.py:21
+    p: float = 1
+    stride: int = 1
+    padding: int = 0
+    dilation: int = 1
+    padding_mode: str = "reflect"
+    similarity: bool = True
+    eps: float = 1e-6
+    q_scs: float = 1e-6
+    difference_taps: bool = False  # nfp.py:74: raw measure string in ('norm','rmse','mahalanobis')
+    path: str = "auto"             # 'auto' | 'generic' | 'fused'
+
+    @property
+    def kernel_size(self) -> int:
+        return 2 * self.R + 1
+
+    @property
+    def out_channels(self) -> int:
+        return self.kernel_size ** 2 - 1
+
+
+def conv_output_size(n: int, cfg: NFPConfig) -> int:
+    """Conv2d output-size rule (what nfp.py:128-129 restates)."""
+    return (n + 2 * cfg.padding - cfg.dilation * (cfg.kernel_size - 1) - 1) // cfg.stride + 1
+
+
+def _check_geometry(H: int, W: int, cfg: NFPConfig):
+    # same failure modes as the reference's Conv2d(padding_mode=...) forward
+    if cfg.padding_mode == "reflect" and cfg.padding > 0 and (cfg.padding >= H or cfg.padding >= W):
+        raise RuntimeError(
+            "Padding size should be less than the corresponding input dimension, but got: padding "
+            f"({cfg.padding}, {cfg.padding}) at dimension 3 of input {[H, W]}")
+    if cfg.padding_mode == "circular" and (cfg.padding > H or cfg.padding > W):
+        raise RuntimeError("Padding value causes wrapping around more than once.")
+    Ho, Wo = conv_output_size(H, cfg), conv_output_size(W, cfg)
+    if Ho <= 0 or Wo <= 0:
+        span = cfg.dilation * (cfg.kernel_size - 1) + 1
+        raise RuntimeError(
+            f"Calculated padded input size per channel: ({H + 2 * cfg.padding} x {W + 2 * cfg.padding}). "
+            f"Kernel size: ({span} x {span}). Kernel size can't be greater than actual input size")
+    return Ho, Wo
+
+
+def shape_probe(x: torch.Tensor, cfg: NFPConfig) -> torch.Tensor:
+    """Answer a constructor-time shape probe without computing anything.
+
+    The reference heads discover NFP's output width by running a CPU dummy
+    through the layer inside ``__init__`` under ``torch.no_grad()``
+    (resnet18.py:22-25, nfp_heads.py:24-27, mobilenetv3.py:337-353).  This
+    package has no CPU implementation, so a CPU input with autograd disabled is
+    answered with a NaN-filled tensor of the correct shape: ``.shape`` is all
+    those callers read, and any accidental use of the values is loud.
+    """
+    B, C, H, W = x.shape
+    Ho, Wo = _check_geometry(H, W, cfg)
+    return torch.full((B, cfg.out_channels, Ho, Wo), float("nan"), dtype=x.dtype, device=x.device)
+
+
+def _reject_cpu(x: torch.Tensor):
+    raise RuntimeError(
+        "neighbour_feature_pooling_b200 runs only on CUDA (sm_100a) tensors; got a "
+        f"{x.device.type} tensor.  There is no CPU fallback by design.  (CPU inputs are accepted only "
+        "as shape probes under torch.no_grad().)")
+
+
+_KERNEL_DTYPES = {torch.float32: _capi.F32, torch.bfloat16: _capi.BF16}
+
+
+def _prepare(x: torch.Tensor):
+    """-> (tensor in a kernel dtype, dtype to return results in)"""
+    if x.dim() != 4:
+        raise RuntimeError(f"NFP expects a 4-D (B, C, H, W) input, got {tuple(x.shape)}")
+    if not x.is_floating_point():
+        raise RuntimeError(f"NFP expects a floating-point input, got {x.dtype}")
+    out_dtype = x.dtype
+    if torch.is_autocast_enabled("cuda") and x.dtype == torch.float32:
+        # the reference's depthwise convs run in the autocast dtype (nfp.py:152-153)
+        out_dtype = torch.get_autocast_dtype("cuda")
+        x = x.to(out_dtype)
+    if x.dtype == torch.float64:
+        raise RuntimeError("NFP kernels compute in fp32; float64 inputs are not supported")
+    if x.dtype not in _KERNEL_DTYPES:  # fp16: widen, the kernels accumulate in fp32 anyway
+        x = x.float()
+    return x.contiguous(), out_dtype
+
+
+def _desc_for(x: torch.Tensor, cfg: NFPConfig) -> _capi.Desc:
+    B, C, H, W = x.shape
+    return _capi.make_desc(_KERNEL_DTYPES[x.dtype], B, C, H, W, cfg.R, cfg.stride, cfg.padding,
+                           cfg.dilation, cfg.padding_mode, cfg.measure, cfg.similarity,
+                           cfg.difference_taps, cfg.eps, cfg.p, cfg.q_scs, cfg.path)
+
+
+def _workspace(desc, op, device):
+    n = _capi.workspace_bytes(desc, op)
+    if n == 0:
+        return None, 0, 0
+    ws = torch.empty(n, dtype=torch.uint8, device=device)
+    return ws, ws.data_ptr(), n
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _NFPSimilarity(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cfg):
+        desc = _desc_for(x, cfg)
+        Ho, Wo = _capi.output_shape(desc)
+        y = torch.empty((x.shape[0], cfg.out_channels, Ho, Wo), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            ws, ws_ptr, ws_n = _workspace(desc, _capi.OP_FORWARD, x.device)
+            rc = _capi.load().nfpb200_forward(ctypes.byref(desc), x.data_ptr(), y.data_ptr(), ws_ptr, ws_n,
+                                              _stream(x.device))
+        _capi.check(rc, "nfpb200_forward")
+        ctx.save_for_backward(x)
+        ctx.cfg = cfg
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        desc = _desc_for(x, ctx.cfg)
+        gy = gy.to(x.dtype).contiguous()
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            ws, ws_ptr, ws_n = _workspace(desc, _capi.OP_BACKWARD, x.device)
+            rc = _capi.load().nfpb200_backward(ctypes.byref(desc), x.data_ptr(), gy.data_ptr(), gx.data_ptr(),
+                                               ws_ptr, ws_n, _stream(x.device))
+        _capi.check(rc, "nfpb200_backward")
+        return gx, None
+
+
+class _NFPGapPair(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cfg):
+        desc = _desc_for(x, cfg)
+        B, C = x.shape[:2]
+        gap_x = torch.empty((B, C), dtype=torch.float32, device=x.device)
+        gap_nfp = torch.empty((B, cfg.out_channels), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            ws, ws_ptr, ws_n = _workspace(desc, _capi.OP_POOL_FORWARD, x.device)
+            rc = _capi.load().nfpb200_pool_forward(ctypes.byref(desc), x.data_ptr(), gap_x.data_ptr(),
+                                                   gap_nfp.data_ptr(), ws_ptr, ws_n, _stream(x.device))
+        _capi.check(rc, "nfpb200_pool_forward")
+        ctx.save_for_backward(x)
+        ctx.cfg = cfg
+        return gap_x.to(x.dtype), gap_nfp.to(x.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_gap_x, g_gap_nfp):
+        (x,) = ctx.saved_tensors
+        desc = _desc_for(x, ctx.cfg)
+        g_gap_x = g_gap_x.float().contiguous()
+        g_gap_nfp = g_gap_nfp.float().contiguous()
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            ws, ws_ptr, ws_n = _workspace(desc, _capi.OP_POOL_BACKWARD, x.device)
+            rc = _capi.load().nfpb200_pool_backward(ctypes.byref(desc), x.data_ptr(), g_gap_x.data_ptr(),
+                                                    g_gap_nfp.data_ptr(), gx.data_ptr(), ws_ptr, ws_n,
+                                                    _stream(x.device))
+        _capi.check(rc, "nfpb200_pool_backward")
+        return gx, None
+
+
+def nfp_similarity(x: torch.Tensor, cfg: NFPConfig) -> torch.Tensor:
+    """(B, C, H, W) -> (B, k*k-1, H', W') similarity map; differentiable w.r.t. ``x``."""
+    if x.device.type != "cuda":
+        if x.device.type == "cpu" and not torch.is_grad_enabled():
+            return shape_probe(x, cfg)
+        _reject_cpu(x)
+    if x.dim() == 4:
+        _check_geometry(x.shape[2], x.shape[3], cfg)
+    xk, out_dtype = _prepare(x)
+    y = _NFPSimilarity.apply(xk, cfg)
+    return y if y.dtype == out_dtype else y.to(out_dtype)
+
+
+def nfp_gap_pair(x: torch.Tensor, cfg: NFPConfig):
+    """``(GAP(x), GAP(NFP(x)))`` -> ((B, C), (B, k*k-1)) in one pass over ``x``."""
+    if x.device.type != "cuda":
+        _reject_cpu(x)
+    if x.dim() == 4:
+        _check_geometry(x.shape[2], x.shape[3], cfg)
+    xk, out_dtype = _prepare(x)
+    gx, gn = _NFPGapPair.apply(xk, cfg)
+    if gx.dtype != out_dtype:
+        gx, gn = gx.to(out_dtype), gn.to(out_dtype)
+    return gx, gn
+
+
+def describe(x_shape, dtype: torch.dtype, cfg: NFPConfig, op: int = _capi.OP_FORWARD) -> str:
+    """Name of the kernel path a problem would take (for tests / bench reporting)."""
+    B, C, H, W = x_shape
+    desc = _capi.make_desc(_KERNEL_DTYPES[dtype], B, C, H, W, cfg.R, cfg.stride, cfg.padding, cfg.dilation,
+                           cfg.padding_mode, cfg.measure, cfg.similarity, cfg.difference_taps, cfg.eps,
+                           cfg.p, cfg.q_scs, cfg.path)
+    return _capi.describe_path(desc, op)
+
+
+__all__ = ["NFPConfig", "nfp_similarity", "nfp_gap_pair", "shape_probe", "conv_output_size", "describe",
+           "replace", "math"]
