@@ -1,0 +1,508 @@
+#!/usr/bin/env python
+"""NFP hot-path benchmark (BASELINE.json metric: NFP fwd+bwd feature-maps/s & % of the HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--shape l4|l3|mbv3|vit|eurosat] [--R 1|2] [--dtype fp32|bf16] [--batch 256] [--no-sweep]
+
+One "step" = one forward + one backward of the NFP layer (cosine, pad = R, reflect) over one batch
+of synthetic feature maps.  Default workload: BASELINE.json configs[1], ResNet18 layer4 maps
+(B=256, 512x7x7, 3x3, fp32).  Prints ONE JSON line (rank 0).
+
+* ``value``    -- maps/s, inputs resident in HBM, the C-ABI entry points launched back to back from a
+                  CUDA graph; buffers rotate over > 2x the L2 capacity so every step reads from HBM.
+* ``e2e``      -- the same metric through the public nn.Module API (``NFPPooling`` + autograd) with
+                  HOST pinned buffers: H2D of x and grad_y and D2H of y and grad_x inside the timed region.
+* ``roofline`` -- the dominant kernel (backward): algorithmic bytes per launch / its average launch
+                  duration (CUDA events around a graph of back-to-back launches on rotating buffers).
+* ``cpu_baseline`` -- the conv-form CPU port of the reference (oracle/nfp_convform.py) on the host cores.
+* ``--impl reference`` -- that CPU port as its own arm, same metric / config.
+
+Multi-GPU (torchrun): the batch dimension is sharded, one process per GPU, no data-path collective;
+weak scaling (B maps per GPU per step); time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SHAPES = {  # name -> (C, H, W, where it comes from)
+    "l4": (512, 7, 7, "ResNet18 layer4"),
+    "l3": (256, 14, 14, "ResNet18 layer3"),
+    "mbv3": (960, 7, 7, "MobileNetV3-large last stage"),
+    "vit": (192, 14, 14, "ViT-Tiny token grid"),
+    "eurosat": (512, 2, 2, "ResNet18 layer4 at 64x64 input"),
+}
+L2_BYTES = 126 * 1024 * 1024
+METRIC = "nfp_fwd_bwd_feature_maps_per_s"
+UNIT = "maps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--shape", default="l4", choices=sorted(SHAPES))
+    ap.add_argument("--R", type=int, default=1)
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--no-sweep", action="store_true", help="skip the table over the other configs[1] cases")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline budget (seconds of CPU work)")
+    return ap.parse_args()
+
+
+def algorithmic_bytes(B, C, H, W, R, esz):
+    """SURVEY.md 8(d3).  Per launch: forward reads x, writes y; backward reads x and grad_y, writes grad_x."""
+    K = (2 * R + 1) ** 2 - 1
+    fwd = B * (C * H * W + K * H * W) * esz
+    bwd = B * (2 * C * H * W + K * H * W) * esz
+    return fwd, bwd
+
+
+def workload_name(B, C, H, W, R, dtype):
+    k = 2 * R + 1
+    return f"nfp_cosine_fwd_bwd B={B} {C}x{H}x{W} {k}x{k} pad={R} reflect {dtype}"
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks: NVML polled from a thread while a timed region runs
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, dev):
+        self.ok = False
+        self.samples = []   # (tag, sm_mhz, reasons_mask)
+        self.tag = None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            try:   # CUDA ordinal != NVML index under CUDA_VISIBLE_DEVICES: resolve by UUID
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(dev.index or 0)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # NVML missing: report that, do not fake numbers
+            self.err = repr(e)
+            self.sm_max = None
+        self.thread = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            tag = self.tag
+            if tag is not None:
+                try:
+                    mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.samples.append((tag, mhz, mask))
+                except Exception:
+                    pass
+            time.sleep(0.001)
+
+    def start(self):
+        if self.ok:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.thread:
+            self.thread.join(timeout=1.0)
+
+    def summary(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": self.err}
+        main = [s for s in self.samples if s[0] == "timed"]
+        window = "timed region"
+        if len(main) < 3:
+            main = [s for s in self.samples if s[0] is not None]
+            window = "all timed regions (value, kernel passes, e2e)"
+        mhz = sorted(s[1] for s in main)
+        mask = 0
+        for s in main:
+            mask |= s[2]
+        reasons = [name for bit, name in self.REASONS.items() if mask & bit and name != "gpu_idle"]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(main), "window": window}
+
+
+# ----------------------------------------------------------------------------------------------
+# the B200 arm
+# ----------------------------------------------------------------------------------------------
+class LayerBench:
+    """Rotating device buffers + C-ABI launches for one (shape, R, dtype) configuration."""
+
+    def __init__(self, dev, B, C, H, W, R, dtype_name, seed=0):
+        from neighbour_feature_pooling_b200 import _capi
+        self.capi = _capi
+        self.lib = _capi.load()
+        self.dev = dev
+        self.B, self.C, self.H, self.W, self.R = B, C, H, W, R
+        self.K = (2 * R + 1) ** 2 - 1
+        self.tdtype = torch.float32 if dtype_name == "fp32" else torch.bfloat16
+        self.esz = 4 if dtype_name == "fp32" else 2
+        self.desc = _capi.make_desc(_capi.F32 if dtype_name == "fp32" else _capi.BF16, B, C, H, W, R, 1, R, 1,
+                                    "reflect", "cosine", True, False, 1e-6, 1, 1e-6, "auto")
+        self.path_fwd = _capi.describe_path(self.desc, _capi.OP_FORWARD)
+        self.path_bwd = _capi.describe_path(self.desc, _capi.OP_BACKWARD)
+        self.launches = _capi.launch_count(self.desc, _capi.OP_FORWARD) + _capi.launch_count(self.desc, _capi.OP_BACKWARD)
+        set_bytes = (2 * B * C * H * W + 2 * B * self.K * H * W) * self.esz
+        self.set_bytes = set_bytes
+        self.nbuf = max(4, math.ceil(2.2 * L2_BYTES / set_bytes))
+        gen = torch.Generator(device=dev).manual_seed(seed)
+        mk = lambda *s: torch.randn(*s, device=dev, generator=gen).to(self.tdtype)
+        self.x = [mk(B, C, H, W) for _ in range(self.nbuf)]
+        self.gy = [mk(B, self.K, H, W) for _ in range(self.nbuf)]
+        self.y = [torch.empty(B, self.K, H, W, device=dev, dtype=self.tdtype) for _ in range(self.nbuf)]
+        self.gx = [torch.empty(B, C, H, W, device=dev, dtype=self.tdtype) for _ in range(self.nbuf)]
+        wsf = _capi.workspace_bytes(self.desc, _capi.OP_FORWARD)
+        wsb = _capi.workspace_bytes(self.desc, _capi.OP_BACKWARD)
+        self.ws = torch.empty(max(wsf, wsb, 1), dtype=torch.uint8, device=dev)
+        self.ws_n = max(wsf, wsb)
+
+    def fwd(self, i):
+        s = torch.cuda.current_stream(self.dev).cuda_stream
+        rc = self.lib.nfpb200_forward(ctypes.byref(self.desc), self.x[i].data_ptr(), self.y[i].data_ptr(),
+                                      self.ws.data_ptr() if self.ws_n else None, self.ws_n, s)
+        self.capi.check(rc, "nfpb200_forward")
+
+    def bwd(self, i):
+        s = torch.cuda.current_stream(self.dev).cuda_stream
+        rc = self.lib.nfpb200_backward(ctypes.byref(self.desc), self.x[i].data_ptr(), self.gy[i].data_ptr(),
+                                       self.gx[i].data_ptr(), self.ws.data_ptr() if self.ws_n else None,
+                                       self.ws_n, s)
+        self.capi.check(rc, "nfpb200_backward")
+
+    def step(self, i):
+        self.fwd(i)
+        self.bwd(i)
+
+    def _graph(self, fn, n, start):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for j in range(n):
+                fn((start + j) % self.nbuf)
+        return g
+
+    def timed(self, fn, steps, warmup, sampler=None, tag=None, barrier=None, chunk=250):
+        """Run `warmup` untimed then EXACTLY `steps` timed calls of fn (graph replays); returns seconds."""
+        for j in range(max(warmup, 3)):
+            fn(j % self.nbuf)
+        torch.cuda.synchronize(self.dev)
+        plan, done = [], 0
+        graphs = {}
+        while done < steps:
+            n = min(chunk, steps - done)
+            key = (n, done % self.nbuf)
+            if key not in graphs:
+                graphs[key] = self._graph(fn, n, done % self.nbuf)
+            plan.append(graphs[key])
+            done += n
+        plan[0].replay()     # graph upload / first-replay cost stays outside the timed region
+        torch.cuda.synchronize(self.dev)
+        if barrier:
+            barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.tag = tag
+        torch.cuda.synchronize(self.dev)
+        e0.record()
+        for g in plan:
+            g.replay()
+        e1.record()
+        e1.synchronize()
+        if sampler:
+            sampler.tag = None
+        torch.cuda.synchronize(self.dev)
+        return e0.elapsed_time(e1) * 1e-3
+
+
+def e2e_through_module(dev, B, C, H, W, R, dtype_name, steps, warmup, sampler, barrier):
+    """Public-API path with host buffers: H2D(x, gy) -> NFPPooling fwd -> autograd bwd -> D2H(y, gx)."""
+    import neighbour_feature_pooling_b200 as nfpb
+    tdtype = torch.float32 if dtype_name == "fp32" else torch.bfloat16
+    K = (2 * R + 1) ** 2 - 1
+    layer = nfpb.NFPPooling(C, R=R, measure="cosine", padding=R).to(dev)
+    gen = torch.Generator().manual_seed(1)
+    nh = 2  # two host buffer sets, alternated
+    hx = [torch.randn(B, C, H, W, generator=gen).to(tdtype).pin_memory() for _ in range(nh)]
+    hg = [torch.randn(B, K, H, W, generator=gen).to(tdtype).pin_memory() for _ in range(nh)]
+    hy = [torch.empty(B, K, H, W, dtype=tdtype).pin_memory() for _ in range(nh)]
+    hgx = [torch.empty(B, C, H, W, dtype=tdtype).pin_memory() for _ in range(nh)]
+
+    def one(i):
+        x = hx[i % nh].to(dev, non_blocking=True).requires_grad_(True)
+        g = hg[i % nh].to(dev, non_blocking=True)
+        y = layer(x)
+        y.backward(g)
+        hy[i % nh].copy_(y.detach(), non_blocking=True)
+        hgx[i % nh].copy_(x.grad, non_blocking=True)
+
+    for i in range(max(3, warmup)):
+        one(i)
+    torch.cuda.synchronize(dev)
+    if barrier:
+        barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.tag = "e2e"
+    e0.record()
+    for i in range(steps):
+        one(i)
+    e1.record()
+    e1.synchronize()
+    sampler.tag = None
+    esz = 4 if dtype_name == "fp32" else 2
+    h2d = (B * C * H * W + B * K * H * W) * esz
+    d2h = h2d
+    return e0.elapsed_time(e1) * 1e-3, h2d, d2h, float(hy[0].float().abs().sum())
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the conv-form port of the reference on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_port_setup(C, H, W, R, dtype_name, B):
+    from oracle.nfp_convform import ConvFormCosineNFP, forward_backward  # the only product-side use of oracle/
+    tdtype = torch.float32 if dtype_name == "fp32" else torch.bfloat16
+    K = (2 * R + 1) ** 2 - 1
+    layer = ConvFormCosineNFP(C, R=R, padding=R).to(tdtype)
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(B, C, H, W, generator=gen).to(tdtype)
+    g = torch.randn(B, K, H, W, generator=gen).to(tdtype)
+    return lambda: forward_backward(layer, x, g)
+
+
+def cpu_threads():
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return n
+
+
+def cpu_baseline(C, H, W, R, dtype_name, B, budget_s):
+    cores = cpu_threads()
+    Bs = min(B, 32)
+    run = cpu_port_setup(C, H, W, R, dtype_name, Bs)
+    run()
+    t0 = time.perf_counter(); run(); dt = time.perf_counter() - t0
+    rate = Bs / dt
+    # size the timed sample to ~budget_s of wall time (x cores of CPU work), at most the full batch
+    Bt = int(max(1, min(B, rate * budget_s / 3)))
+    run = cpu_port_setup(C, H, W, R, dtype_name, Bt)
+    run()
+    reps, t = 0, 0.0
+    while reps < 3 or (t < budget_s and reps < 10):
+        t0 = time.perf_counter(); run(); t += time.perf_counter() - t0
+        reps += 1
+        if t > 2 * budget_s:
+            break
+    return {"value": reps * Bt / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{reps} x fwd+bwd of B={Bt} maps (same shape/dtype), conv-form port of the reference "
+                      f"(oracle/nfp_convform.py: reflect-pad + one-hot depthwise conv + F.cosine_similarity + autograd), "
+                      f"torch {torch.__version__} CPU, {cores} threads, {t:.1f} s"}
+
+
+def run_reference_arm(args, C, H, W, where):
+    """--impl reference: the reference's CPU algorithm (conv-form port) as its own arm; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = cpu_threads()
+    B = args.batch
+    probe = cpu_port_setup(C, H, W, args.R, args.dtype, min(B, 16))
+    probe()
+    t0 = time.perf_counter(); probe(); rate = min(B, 16) / (time.perf_counter() - t0)
+    total = args.steps + args.warmup
+    Bs = int(max(1, min(B, rate * 150.0 / max(total, 1))))   # whole run within a few minutes
+    run = cpu_port_setup(C, H, W, args.R, args.dtype, Bs)
+    for _ in range(args.warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt = time.perf_counter() - t0
+    value = args.steps * Bs / dt
+    sample = (f"each step = fwd+bwd of B={Bs} maps (bounded sample of the B={B} batch), conv-form port of the "
+              f"reference's ATen chain (oracle/nfp_convform.py), torch {torch.__version__} CPU, {cores} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.dtype == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(B, C, H, W, args.R, args.dtype), "source": where,
+                       "batch_per_step": Bs, "note": "the Python reference cannot travel to the GPU box; this is its "
+                                                     "operator sequence restated (kind=port), run on the host cores only"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    C, H, W, where = SHAPES[args.shape]
+    if args.impl == "reference":
+        run_reference_arm(args, C, H, W, where)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=b200) needs a CUDA device: the NFP operator has no CPU fallback")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(t):
+        if dist is None:
+            return t
+        v = torch.tensor([t], device=dev, dtype=torch.float64)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v.item())
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+    B, R = args.batch, args.R
+    sampler = ClockSampler(dev)
+    sampler.start()
+
+    lb = LayerBench(dev, B, C, H, W, R, args.dtype)
+    # ---- value: K steps of fwd+bwd, device resident, HBM-cold via buffer rotation -------------------
+    t_step_total = lb.timed(lb.step, args.steps, args.warmup, sampler, "timed", barrier)
+    t_step_total = max_over_ranks(t_step_total)
+    value = world * args.steps * B / t_step_total
+    # ---- per-kernel launch durations (same rotation, back-to-back launches of one kernel) ---------
+    sampler_tag = "kernels"
+    t_fwd = lb.timed(lb.fwd, args.steps, args.warmup, sampler, sampler_tag) / args.steps
+    t_bwd = lb.timed(lb.bwd, args.steps, args.warmup, sampler, sampler_tag) / args.steps
+    fwd_bytes, bwd_bytes = algorithmic_bytes(B, C, H, W, R, lb.esz)
+    # ---- e2e through the nn.Module API with host buffers ------------------------------------------------
+    e2e_steps = min(args.steps, 50)
+    t_e2e, h2d, d2h, _chk = e2e_through_module(dev, B, C, H, W, R, args.dtype, e2e_steps, min(args.warmup, 5),
+                                               sampler, barrier)
+    t_e2e = max_over_ranks(t_e2e)
+    e2e_value = world * e2e_steps * B / t_e2e
+
+    # ---- the other configs[1] cases (reported, not part of `value`) -------------------------------------
+    sweep = []
+    if not args.no_sweep and rank == 0:
+        for shp in ("l4", "l3"):
+            for r in (1, 2):
+                for dt in ("fp32", "bf16"):
+                    c, h, w, _ = SHAPES[shp]
+                    s = LayerBench(dev, B, c, h, w, r, dt)
+                    n = min(args.steps, 200)
+                    tt = s.timed(s.step, n, 5, sampler, "sweep") / n
+                    tf = s.timed(s.fwd, n, 5, sampler, "sweep") / n
+                    tb = s.timed(s.bwd, n, 5, sampler, "sweep") / n
+                    fb, bb = algorithmic_bytes(B, c, h, w, r, s.esz)
+                    sweep.append({"workload": workload_name(B, c, h, w, r, dt), "maps_per_s": B / tt,
+                                  "us_per_step": tt * 1e6, "us_fwd": tf * 1e6, "us_bwd": tb * 1e6,
+                                  "step_gbs": (fb + bb) / tt / 1e9, "step_frac": (fb + bb) / tt / 1e9 / hbm_peak,
+                                  "bwd_frac": bb / tb / 1e9 / hbm_peak, "fwd_frac": fb / tf / 1e9 / hbm_peak,
+                                  "path": s.path_bwd})
+                    del s
+                    torch.cuda.empty_cache()
+    sampler.stop()
+    barrier()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(C, H, W, R, args.dtype, B, args.cpu_seconds)
+
+    if rank == 0:
+        achieved = bwd_bytes / t_bwd / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_step_total / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.dtype == "fp32" else "bf16",
+            "data": "synthetic",
+            "config": {"workload": workload_name(B, C, H, W, R, args.dtype), "source": where,
+                       "batch_per_gpu": B, "global_batch": B * world, "sharding": f"batch over {world} GPU(s), no collective",
+                       "l2_hygiene": f"inputs/outputs rotate over {lb.nbuf} buffer sets "
+                                     f"({lb.nbuf * lb.set_bytes / 2**20:.0f} MiB > 2x the 126 MiB L2), so every step is HBM-cold",
+                       "launch": "CUDA graph of C-ABI launches (nfpb200_forward + nfpb200_backward per step)",
+                       "kernel_path": {"forward": lb.path_fwd, "backward": lb.path_bwd}},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": t_e2e / e2e_steps * 1e3,
+                    "api": "NFPPooling(C,R,'cosine',padding=R).forward + autograd backward; pinned host x, grad_y -> "
+                           "device; y, grad_x -> pinned host"},
+            "gpu_launches": args.steps * lb.launches,
+            "roofline": {"bound": "hbm", "kernel": "nfpb200_backward (" + lb.path_bwd + ")", "achieved": achieved,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                         "peak_source": peak_src, "bytes_per_launch": bwd_bytes, "us_per_launch": t_bwd * 1e6},
+            "roofline_forward": {"kernel": "nfpb200_forward (" + lb.path_fwd + ")", "achieved": fwd_bytes / t_fwd / 1e9,
+                                 "frac": fwd_bytes / t_fwd / 1e9 / hbm_peak, "bytes_per_launch": fwd_bytes,
+                                 "us_per_launch": t_fwd * 1e6},
+            "roofline_step": {"achieved": (fwd_bytes + bwd_bytes) * args.steps / t_step_total / 1e9,
+                              "frac": (fwd_bytes + bwd_bytes) * args.steps / t_step_total / 1e9 / hbm_peak,
+                              "bytes_per_step": fwd_bytes + bwd_bytes,
+                              "bwd_share_of_step": t_bwd / (t_fwd + t_bwd)},
+            "clocks": sampler.summary(),
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if sweep:
+            line["sweep"] = sweep
+        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+        try:  # dram bytes per launch from the committed ncu --set full capture of this kernel, if any
+            with open(traffic_file) as f:
+                tr = json.load(f)
+            key = workload_name(B, C, H, W, R, args.dtype)
+            if key in tr:
+                line["roofline"]["traffic"] = tr[key]["backward_dram_bytes"]
+                line["roofline"]["traffic_source"] = tr[key].get("source")
+        except Exception:
+            pass
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

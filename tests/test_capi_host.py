@@ -1,0 +1,81 @@
+"""CPU: the C-ABI library loads, exports every symbol include/nfp_b200.h declares, and its host-only
+entry points (shape / workspace / path queries, argument validation) behave.  No compute calls."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from neighbour_feature_pooling_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _desc(**kw):
+    base = dict(dtype=_capi.F32, B=2, C=8, H=7, W=7, R=1, stride=1, padding=1, dilation=1,
+                padding_mode="reflect", measure="cosine", similarity=True, difference_taps=False,
+                eps=1e-6, p=1, q_scs=1e-6, path="auto")
+    base.update(kw)
+    return _capi.make_desc(**base)
+
+
+def test_header_symbols_are_exported():
+    with open(os.path.join(ROOT, "include", "nfp_b200.h")) as f:
+        header = f.read()
+    declared = sorted(set(re.findall(r"\b(nfpb200_[a-z_]+)\s*\(", header)))
+    assert declared, "no entry points found in the header"
+    lib = _capi.load()
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/nfp_b200.h but not exported"
+    assert sorted(_capi.EXPORTS) == declared
+    assert lib.nfpb200_abi_version() == _capi.ABI_VERSION == int(re.search(r"NFPB200_ABI_VERSION (\d+)", header).group(1))
+
+
+def test_desc_struct_matches_header_layout():
+    # 18 x 4-byte fields, no padding
+    assert ctypes.sizeof(_capi.Desc) == 72
+
+
+def test_output_shape_rule():
+    assert _capi.output_shape(_desc()) == (7, 7)
+    assert _capi.output_shape(_desc(H=14, W=9, R=2, padding=2)) == (14, 9)
+    assert _capi.output_shape(_desc(H=8, W=7, stride=2)) == (4, 4)
+    assert _capi.output_shape(_desc(H=9, W=9, dilation=2, padding=2)) == (9, 9)
+    assert _capi.output_shape(_desc(H=5, W=5, padding=0)) == (3, 3)
+
+
+def test_argument_errors():
+    lib = _capi.load()
+    ho, wo = ctypes.c_int32(), ctypes.c_int32()
+    d = _desc(H=2, W=2, padding=2)  # reflect pad >= dim
+    assert lib.nfpb200_output_shape(ctypes.byref(d), ctypes.byref(ho), ctypes.byref(wo)) == -2
+    assert "Padding size should be less" in _capi.status_string(-2)
+    d = _desc(H=2, W=2, padding=0)  # window larger than input
+    assert lib.nfpb200_output_shape(ctypes.byref(d), ctypes.byref(ho), ctypes.byref(wo)) == -3
+    d = _desc()
+    d.struct_bytes = 10
+    assert lib.nfpb200_output_shape(ctypes.byref(d), ctypes.byref(ho), ctypes.byref(wo)) == -1
+    d = _desc()
+    d.measure = 99
+    assert lib.nfpb200_output_shape(ctypes.byref(d), ctypes.byref(ho), ctypes.byref(wo)) == -1
+    # null data pointers are rejected before anything touches the device
+    assert lib.nfpb200_forward(ctypes.byref(_desc()), None, None, None, 0, None) == -1
+    with pytest.raises(RuntimeError, match="invalid argument"):
+        _capi.check(-1, "x")
+
+
+def test_path_selection_and_workspace():
+    fused = _desc(B=256, C=512)
+    assert _capi.describe_path(fused, _capi.OP_FORWARD).startswith("fused/")
+    assert _capi.workspace_bytes(fused, _capi.OP_BACKWARD) == 0
+    assert _capi.launch_count(fused, _capi.OP_FORWARD) == 1
+    assert _capi.launch_count(fused, _capi.OP_BACKWARD) == 1
+    generic = _desc(B=4, C=8, H=9, W=9, stride=2)
+    assert _capi.describe_path(generic, _capi.OP_FORWARD) == "generic/pairs"
+    assert _capi.workspace_bytes(generic, _capi.OP_BACKWARD) > 0
+    forced = _desc(B=4, C=8, H=9, W=9, stride=2, path="fused")
+    n = ctypes.c_size_t()
+    assert _capi.load().nfpb200_workspace_bytes(ctypes.byref(forced), _capi.OP_FORWARD, ctypes.byref(n)) == -5
+    # every measure has a generic path
+    for m in _capi.MEASURES:
+        assert _capi.describe_path(_desc(measure=m, path="generic"), _capi.OP_BACKWARD) == "generic/pairs"

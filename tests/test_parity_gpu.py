@@ -1,0 +1,240 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the reference.
+
+* every golden case generated from the unmodified reference (tests/golden/, oracle/make_golden.py):
+  all 17 measures + spelling quirks, 3x3 / 5x5, stride / dilation / pad != R, reflect / zeros;
+* seeded random inputs against the oracle over a geometry x measure grid (generic kernels) and over
+  the fused-kernel shapes;
+* size-independent properties at BASELINE.json's full sizes (B=256, 512x7x7 / 256x14x14).
+
+Tolerances (BASELINE.json north_star): fp32 <= 1e-5 relative (max-norm), bf16 <= 2e-2 against the
+fp32/fp64 reference evaluated on the bf16-rounded input.
+"""
+import numpy as np
+import pytest
+import torch
+
+import neighbour_feature_pooling_b200 as nfpb
+from neighbour_feature_pooling_b200 import NFPPooling, nfp_pooling, functional as NF
+from oracle import nfp_oracle as O
+
+from _util import case_id, case_kwargs, load_measure_cases, load_wrapper_cases, rel_err
+
+pytestmark = pytest.mark.gpu
+
+INDEX, ARR = load_measure_cases()
+FP32_TOL = 1e-5
+BF16_TOL = 2e-2
+# measures whose fp32 evaluation is ill-conditioned by construction (log / sqrt of eps-shifted values,
+# divisions by eps-sized denominators): the reference's own fp32 run is not 1e-5-close to its fp64 run.
+LOOSE = {"jeffrey": 2e-4, "hellinger": 1e-4, "squaredchord": 1e-4, "canberra": 1e-4, "chisquared1": 1e-4,
+         "chisquared2": 1e-4, "geman": 1e-4, "pearson": 5e-5, "scs": 1e-4, "sharpened_cosine": 1e-4,
+         "smith": 5e-5, "rmse": 5e-5, "norm": 5e-5, "gfc": 2e-5, "attention": 5e-5}
+
+
+def _run(x, g, kw, dev, dtype=torch.float32, path="auto"):
+    layer = NFPPooling(x.shape[1], **kw).to(dev)
+    layer._cfg = NF.replace(layer._cfg, path=path)
+    xd = x.to(dev, dtype).requires_grad_(True)
+    y = layer(xd)
+    y.backward(g.to(dev, dtype))
+    return y.detach().float().cpu(), xd.grad.float().cpu()
+
+
+@pytest.mark.parametrize("c", INDEX, ids=case_id)
+def test_golden_fp32(c, cuda_device):
+    x = torch.from_numpy(ARR[c["key"] + "_x"])
+    g = torch.from_numpy(ARR[c["key"] + "_g"])
+    tol = LOOSE.get(c["measure"].lower(), FP32_TOL)
+    for path in ("auto", "generic"):
+        y, gx = _run(x, g, case_kwargs(c), cuda_device, path=path)
+        gtol = FP32_TOL if c["measure"].lower() == "cosine" else max(tol, 2e-5)
+        assert rel_err(y, ARR[c["key"] + "_y_f64"]) < tol, path
+        assert rel_err(gx, ARR[c["key"] + "_gx_f64"]) < gtol, path
+
+
+@pytest.mark.parametrize("c", [c for c in INDEX if c["measure"] in ("cosine", "dot", "gfc", "emd")], ids=case_id)
+def test_golden_bf16(c, cuda_device):
+    x = torch.from_numpy(ARR[c["key"] + "_x"]).bfloat16().float()   # the bf16-rounded input
+    g = torch.from_numpy(ARR[c["key"] + "_g"]).bfloat16().float()
+    y_ref, gx_ref = O.nfp_forward_backward(x.double(), g.double(), **case_kwargs(c))
+    y, gx = _run(x, g, case_kwargs(c), cuda_device, dtype=torch.bfloat16)
+    assert rel_err(y, y_ref) < BF16_TOL
+    assert rel_err(gx, gx_ref) < BF16_TOL
+
+
+GEOMS = [  # (B, C, H, W, R, stride, padding, dilation, mode)
+    (3, 20, 7, 7, 1, 1, 1, 1, "reflect"),
+    (2, 12, 9, 6, 2, 1, 2, 1, "reflect"),
+    (2, 8, 6, 6, 1, 1, 2, 1, "reflect"),
+    (2, 8, 9, 8, 1, 2, 1, 1, "replicate"),
+    (2, 8, 9, 9, 1, 1, 2, 2, "circular"),
+    (2, 8, 7, 7, 1, 2, 3, 2, "zeros"),
+    (1, 5, 11, 13, 3, 1, 3, 1, "reflect"),     # 7x7 window, odd channel count
+    (2, 16, 112, 112, 1, 1, 1, 1, "reflect"),  # multi-stage MobileNetV3 stem map: large HxW, small C
+]
+
+
+@pytest.mark.parametrize("measure", O.MEASURES)
+@pytest.mark.parametrize("geom", GEOMS, ids=lambda g: "x".join(map(str, g[:8])) + g[8])
+def test_random_vs_oracle_generic(measure, geom, cuda_device):
+    B, C, H, W, R, s, pad, d, mode = geom
+    if H * W > 4096 and measure not in ("cosine", "norm", "dot"):
+        pytest.skip("large map checked for the hot measures only")
+    gen = torch.Generator().manual_seed(hash((measure, geom)) % (2 ** 31))
+    x = torch.randn(B, C, H, W, generator=gen)
+    kw = dict(R=R, measure=measure, p=2 if measure in ("norm", "scs") else 1, stride=s, padding=pad,
+              dilation=d, padding_mode=mode)
+    y_ref = O.nfp_forward(x.double(), **kw)
+    g = torch.randn(y_ref.shape, generator=gen)
+    y_ref, gx_ref = O.nfp_forward_backward(x.double(), g.double(), **kw)
+    y, gx = _run(x, g, kw, cuda_device, path="generic")
+    tol = LOOSE.get(measure, FP32_TOL)
+    assert rel_err(y, y_ref) < tol
+    assert rel_err(gx, gx_ref) < max(tol, 2e-5)
+
+
+FUSED_SHAPES = [(5, 64, 7, 7), (3, 512, 7, 7), (2, 960, 7, 7), (3, 256, 14, 14), (2, 192, 14, 14),
+                (6, 512, 2, 2), (4, 32, 4, 4), (3, 20, 7, 7)]
+
+
+@pytest.mark.parametrize("shape", FUSED_SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("mode", ["reflect", "zeros", "replicate"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_fused_cosine_vs_oracle(shape, mode, dtype, cuda_device):
+    B, C, H, W = shape
+    gen = torch.Generator().manual_seed(B * 1000 + C + H)
+    x = torch.randn(B, C, H, W, generator=gen)
+    if C % 3 == 0:
+        x = x.relu()
+    x[0, :, 0, 0] = 0.0              # exact zero vector: gradient must follow ATen's clamp semantics
+    x[-1, :, H - 1, W - 1] *= 1e-9   # ||x|| < eps
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    kw = dict(R=1, measure="cosine", padding=1, padding_mode=mode)
+    cfg = NFPPooling(C, **kw).config
+    assert NF.describe(shape, dtype, cfg).startswith("fused/"), "shape expected on the fused path"
+    g = torch.randn(B, 8, H, W, generator=gen)
+    if dtype == torch.bfloat16:
+        g = g.bfloat16().float()
+    y_ref, gx_ref = O.nfp_forward_backward(x.double(), g.double(), **kw)
+    y, gx = _run(x, g, kw, cuda_device, dtype=dtype)
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert rel_err(y, y_ref) < tol
+    assert rel_err(gx, gx_ref) < tol
+    if dtype == torch.float32:
+        # and the two CUDA paths agree with each other
+        y2, gx2 = _run(x, g, kw, cuda_device, path="generic")
+        assert rel_err(y, y2) < FP32_TOL and rel_err(gx, gx2) < FP32_TOL
+
+
+def test_wrapper_golden(cuda_device):
+    index, arr = load_wrapper_cases()
+    for c in index:
+        k = c["key"]
+        Params = {"num_ftrs": {"m": c["C"]}, "Model_name": "m", "Dataset": "d", "num_classes": {"d": 5}}
+        pool = nfp_pooling(Params=Params)
+        with torch.no_grad():
+            pool.nfp_proj.weight.copy_(torch.from_numpy(arr[k + "_w"]))
+            pool.nfp_proj.bias.copy_(torch.from_numpy(arr[k + "_b"]))
+        pool = pool.to(cuda_device)
+        x = torch.from_numpy(arr[k + "_x"]).to(cuda_device).requires_grad_(True)
+        out = pool(x)
+        out.backward(torch.from_numpy(arr[k + "_g"]).to(cuda_device))
+        assert rel_err(out.detach().cpu(), arr[k + "_out"]) < FP32_TOL
+        assert rel_err(x.grad.cpu(), arr[k + "_gx"]) < FP32_TOL
+        assert rel_err(pool.nfp_proj.weight.grad.cpu(), arr[k + "_gw"]) < FP32_TOL
+        assert rel_err(pool.nfp_proj.bias.grad.cpu(), arr[k + "_gb"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 7, 7), (2, 24, 9, 6)], ids=["fused", "generic"])
+def test_pooled_head_equals_map_then_gap(shape, cuda_device):
+    B, C, H, W = shape
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(B, C, H, W, generator=gen).to(cuda_device)
+    cfg = NFPPooling(C, R=1, measure="cosine", padding=1).config
+    xa = x.clone().requires_grad_(True)
+    ga, gn = NF.nfp_gap_pair(xa, cfg)
+    wa = torch.randn(B, C, generator=gen).to(cuda_device)
+    wn = torch.randn(B, 8, generator=gen).to(cuda_device)
+    ((ga * wa).sum() + (gn * wn).sum()).backward()
+    xb = x.clone().requires_grad_(True)
+    yb = NF.nfp_similarity(xb, cfg)
+    ((xb.mean((2, 3)) * wa).sum() + (yb.mean((2, 3)) * wn).sum()).backward()
+    assert rel_err(ga.detach().cpu(), xb.detach().mean((2, 3)).cpu()) < FP32_TOL
+    assert rel_err(gn.detach().cpu(), yb.detach().mean((2, 3)).cpu()) < FP32_TOL
+    assert rel_err(xa.grad.cpu(), xb.grad.cpu()) < FP32_TOL
+
+
+@pytest.mark.parametrize("C,H,W", [(512, 7, 7), (256, 14, 14)], ids=["layer4", "layer3"])
+@pytest.mark.parametrize("R", [1, 2], ids=["3x3", "5x5"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_full_size_properties(C, H, W, R, dtype, cuda_device):
+    """BASELINE.json config 2 at full size (B=256): properties that need no CPU reference."""
+    B, K = 256, (2 * R + 1) ** 2 - 1
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(B, C, H, W, generator=gen, device=cuda_device).to(dtype)
+    layer = NFPPooling(C, R=R, measure="cosine", padding=R).to(cuda_device)
+    xr = x.clone().requires_grad_(True)
+    y = layer(xr)
+    assert y.shape == (B, K, H, W) and y.dtype == dtype
+    yf = y.detach().float()
+    assert torch.isfinite(yf).all() and yf.abs().max() <= 1.0 + (1e-5 if dtype == torch.float32 else 1e-2)
+    tol = 2e-6 if dtype == torch.float32 else 1e-2
+    # symmetry: tap n at pixel p is the same pair as tap K-1-n at the neighbour (interior pixels)
+    k = 2 * R + 1
+    taps = [(a, b) for a in range(k) for b in range(k) if (a, b) != (R, R)]
+    for n, (a, b) in enumerate(taps):
+        dy, dx = a - R, b - R
+        lhs = yf[:, n, max(0, -dy):H - max(0, dy), max(0, -dx):W - max(0, dx)]
+        rhs = yf[:, K - 1 - n, max(0, dy):H - max(0, -dy), max(0, dx):W - max(0, -dx)]
+        assert (lhs - rhs).abs().max() <= tol
+    # scale invariance of cosine: y(2x) == y(x) exactly (power-of-two scaling is exact in fp)
+    y2 = layer(2 * x)
+    assert torch.equal(y2, y.detach())
+    # per-pixel orthogonality: cosine is invariant to scaling one pixel's vector, so <gx_p, x_p> == 0
+    g = torch.randn(y.shape, generator=gen, device=cuda_device).to(dtype)
+    y.backward(g)
+    gx = xr.grad.float()
+    inner = (gx * x.float()).sum(1)
+    scale = (gx.norm(dim=1) * x.float().norm(dim=1)).clamp_min(1e-20)
+    assert (inner / scale).abs().max() < (1e-4 if dtype == torch.float32 else 3e-2)
+    # linearity of backward in the upstream gradient
+    xr2 = x.clone().requires_grad_(True)
+    layer(xr2).backward(2 * g)
+    assert rel_err(xr2.grad.float().cpu(), (2 * gx).cpu()) < (1e-6 if dtype == torch.float32 else 1e-2)
+    # a slice of the big batch against the oracle
+    y_ref, gx_ref = O.nfp_forward_backward(x[:2].double().cpu(), g[:2].double().cpu(), R=R, measure="cosine", padding=R)
+    ptol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert rel_err(yf[:2].cpu(), y_ref) < ptol
+    assert rel_err(gx[:2].cpu(), gx_ref) < ptol
+
+
+def test_autocast_and_no_grad(cuda_device):
+    layer = NFPPooling(64, R=1, measure="cosine", padding=1).to(cuda_device)
+    x = torch.randn(2, 64, 7, 7, device=cuda_device)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = layer(x)
+    assert y.dtype == torch.bfloat16          # the reference's convs run in the autocast dtype
+    with torch.no_grad():
+        y = layer(x)
+    assert y.dtype == torch.float32 and not y.requires_grad
+    xh = x.half().requires_grad_(True)
+    layer(xh).sum().backward()
+    assert xh.grad.dtype == torch.float16
+    with pytest.raises(RuntimeError, match="float64"):
+        layer(x.double())
+    # non-contiguous (channels_last) input is accepted
+    xc = x.to(memory_format=torch.channels_last)
+    assert rel_err(layer(xc).cpu(), layer(x).cpu()) == 0.0
+
+
+def test_scs_batch_coupling_matches_reference_quirk(cuda_device):
+    """nfp.py:363-374 broadcasts (B,K,H,W)/(B,1,K,H,W): outputs depend on the other batch elements."""
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(4, 6, 5, 5, generator=gen)
+    kw = dict(R=1, measure="scs", p=2, padding=1)
+    y_ref = O.nfp_forward(x.double(), **kw)
+    y, _ = _run(x, torch.zeros_like(y_ref, dtype=torch.float32), kw, cuda_device)
+    assert rel_err(y, y_ref) < 1e-4
+    y_single = O.nfp_forward(x[:1].double(), **kw)
+    assert rel_err(y[:1], y_single) > 1e-3   # genuinely batch-coupled
