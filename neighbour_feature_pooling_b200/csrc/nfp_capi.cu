@@ -2,6 +2,7 @@
 // Validates the descriptor (same error conditions as the reference's Conv2d / reflection_pad2d
 // calls, models/pooling/nfp.py:42-58), picks the fused or the generic kernel path and launches.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "nfp_common.cuh"
@@ -45,12 +46,19 @@ int make_params(const nfpb200_desc_t* d, KParams* out) {
   return NFPB200_OK;
 }
 
-// 1 = fused, 0 = generic, <0 = error
+// 2 = fused/stream, 1 = fused/slab, 0 = generic, <0 = error
 int choose_path(const nfpb200_desc_t* d, const KParams& P, int op) {
-  const bool can = fused_supported(P, d->dtype, d->measure, op);
-  if (d->path == NFPB200_PATH_FUSED) return can ? 1 : NFPB200_EUNSUPPORTED;
+  // NFPB200_FUSED_IMPL=slab selects the first-generation slab kernels (A/B comparisons)
+  static const bool prefer_slab = [] {
+    const char* e = getenv("NFPB200_FUSED_IMPL");
+    return e && strcmp(e, "slab") == 0;
+  }();
+  const bool can_stream = !prefer_slab && stream_supported(P, d->dtype, d->measure, op);
+  const bool can_slab = fused_supported(P, d->dtype, d->measure, op);
+  const int fused = can_stream ? 2 : (can_slab ? 1 : 0);
+  if (d->path == NFPB200_PATH_FUSED) return fused ? fused : NFPB200_EUNSUPPORTED;
   if (d->path == NFPB200_PATH_GENERIC) return 0;
-  return can ? 1 : 0;
+  return fused;
 }
 
 int check_device() {
@@ -103,8 +111,7 @@ int nfpb200_workspace_bytes(const nfpb200_desc_t* desc, int32_t op, size_t* byte
   if (!bytes || op < NFPB200_OP_FORWARD || op > NFPB200_OP_POOL_BACKWARD) return NFPB200_EINVAL;
   int path = choose_path(desc, P, op);
   if (path < 0) return path;
-  *bytes = path ? fused_workspace_bytes(P, desc->dtype, desc->measure, op)
-                : generic_workspace_bytes(P, desc->dtype, desc->measure, op);
+  *bytes = path ? 0 : generic_workspace_bytes(P, desc->dtype, desc->measure, op);
   return NFPB200_OK;
 }
 
@@ -115,7 +122,9 @@ int nfpb200_describe_path(const nfpb200_desc_t* desc, int32_t op, char* buf, siz
   if (!buf || buf_bytes == 0 || op < NFPB200_OP_FORWARD || op > NFPB200_OP_POOL_BACKWARD) return NFPB200_EINVAL;
   int path = choose_path(desc, P, op);
   if (path < 0) return path;
-  snprintf(buf, buf_bytes, "%s", path ? fused_name(P, desc->dtype, desc->measure, op) : "generic/pairs");
+  snprintf(buf, buf_bytes, "%s",
+           path == 2 ? stream_name(P, desc->dtype, desc->measure, op)
+                     : (path == 1 ? fused_name(P, desc->dtype, desc->measure, op) : "generic/pairs"));
   return NFPB200_OK;
 }
 
@@ -126,8 +135,7 @@ int nfpb200_launch_count(const nfpb200_desc_t* desc, int32_t op, int32_t* launch
   if (!launches || op < NFPB200_OP_FORWARD || op > NFPB200_OP_POOL_BACKWARD) return NFPB200_EINVAL;
   int path = choose_path(desc, P, op);
   if (path < 0) return path;
-  *launches = path ? fused_launch_count(P, desc->dtype, desc->measure, op)
-                   : generic_launch_count(P, desc->dtype, desc->measure, op);
+  *launches = path ? 1 : generic_launch_count(P, desc->dtype, desc->measure, op);
   return NFPB200_OK;
 }
 
@@ -139,8 +147,7 @@ int nfpb200_launch_count(const nfpb200_desc_t* desc, int32_t op, int32_t* launch
   if (rc) return rc;                                                                          \
   const int path = choose_path(desc, P, OP);                                                  \
   if (path < 0) return path;                                                                  \
-  const size_t need = path ? fused_workspace_bytes(P, desc->dtype, desc->measure, OP)         \
-                           : generic_workspace_bytes(P, desc->dtype, desc->measure, OP);      \
+  const size_t need = path ? 0 : generic_workspace_bytes(P, desc->dtype, desc->measure, OP);  \
   if (need > 0 && (!workspace || workspace_bytes < need)) return NFPB200_EWORKSPACE;          \
   LaunchCtx ctx{(cudaStream_t)stream, workspace, workspace_bytes};
 
@@ -148,6 +155,7 @@ int nfpb200_forward(const nfpb200_desc_t* desc, const void* x, void* y, void* wo
                     void* stream) {
   if (!x || !y) return NFPB200_EINVAL;
   NFP_PROLOGUE(NFPB200_OP_FORWARD)
+  if (path == 2) return stream_forward(P, desc->dtype, x, y, ctx);
   return path ? fused_forward(P, desc->dtype, x, y, ctx) : generic_forward(P, desc->dtype, desc->measure, x, y, ctx);
 }
 
@@ -155,6 +163,7 @@ int nfpb200_backward(const nfpb200_desc_t* desc, const void* x, const void* gy, 
                      size_t workspace_bytes, void* stream) {
   if (!x || !gy || !gx) return NFPB200_EINVAL;
   NFP_PROLOGUE(NFPB200_OP_BACKWARD)
+  if (path == 2) return stream_backward(P, desc->dtype, x, gy, gx, ctx);
   return path ? fused_backward(P, desc->dtype, x, gy, gx, ctx)
               : generic_backward(P, desc->dtype, desc->measure, x, gy, gx, ctx);
 }
@@ -163,6 +172,7 @@ int nfpb200_pool_forward(const nfpb200_desc_t* desc, const void* x, float* gap_x
                          size_t workspace_bytes, void* stream) {
   if (!x || !gap_x || !gap_nfp) return NFPB200_EINVAL;
   NFP_PROLOGUE(NFPB200_OP_POOL_FORWARD)
+  if (path == 2) return stream_pool_forward(P, desc->dtype, x, gap_x, gap_nfp, ctx);
   return path ? fused_pool_forward(P, desc->dtype, x, gap_x, gap_nfp, ctx)
               : generic_pool_forward(P, desc->dtype, desc->measure, x, gap_x, gap_nfp, ctx);
 }
@@ -171,6 +181,7 @@ int nfpb200_pool_backward(const nfpb200_desc_t* desc, const void* x, const float
                           void* gx, void* workspace, size_t workspace_bytes, void* stream) {
   if (!x || !g_gap_x || !g_gap_nfp || !gx) return NFPB200_EINVAL;
   NFP_PROLOGUE(NFPB200_OP_POOL_BACKWARD)
+  if (path == 2) return stream_pool_backward(P, desc->dtype, x, g_gap_x, g_gap_nfp, gx, ctx);
   return path ? fused_pool_backward(P, desc->dtype, x, g_gap_x, g_gap_nfp, gx, ctx)
               : generic_pool_backward(P, desc->dtype, desc->measure, x, g_gap_x, g_gap_nfp, gx, ctx);
 }

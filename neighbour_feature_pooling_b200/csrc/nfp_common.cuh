@@ -83,4 +83,14 @@ int fused_pool_forward(const KParams& P, int dtype, const void* x, float* gap_x,
 int fused_pool_backward(const KParams& P, int dtype, const void* x, const float* g_gap_x, const float* g_gap_nfp,
                         void* gx, const LaunchCtx& ctx);
 
+// streaming fused kernels (same coverage as the slab kernels, persistent TMA pipeline): nfp_stream.cu
+bool stream_supported(const KParams& P, int dtype, int measure, int op);
+const char* stream_name(const KParams& P, int dtype, int measure, int op);
+int stream_forward(const KParams& P, int dtype, const void* x, void* y, const LaunchCtx& ctx);
+int stream_backward(const KParams& P, int dtype, const void* x, const void* gy, void* gx, const LaunchCtx& ctx);
+int stream_pool_forward(const KParams& P, int dtype, const void* x, float* gap_x, float* gap_nfp,
+                        const LaunchCtx& ctx);
+int stream_pool_backward(const KParams& P, int dtype, const void* x, const float* g_gap_x, const float* g_gap_nfp,
+                         void* gx, const LaunchCtx& ctx);
+
 }  // namespace nfp
