@@ -1,0 +1,45 @@
+// Internal interface between the dtype-specific translation units of the streaming fused kernels
+// (nfp_stream_f32.cu, nfp_stream_bf16.cu) and the dispatcher (nfp_stream.cu).
+#pragma once
+
+#include "nfp_common.cuh"
+
+namespace nfp {
+namespace stream {
+
+enum { MODE_FWD = 0, MODE_BWD = 1, MODE_POOL_FWD = 2, MODE_POOL_BWD = 3 };
+
+struct StreamArgs {
+  const void* x;
+  const void* gy;
+  void* y;
+  void* gx;
+  const float* g_gap_x;
+  const float* g_gap_nfp;
+  float* gap_x;
+  float* gap_nfp;
+  int B, C;
+  int CC;        // channels per chunk (a whole number of group pairs, divides C)
+  int NCH;       // chunks per image
+  int nst;       // ring stages
+  int resident;  // backward: the image fits in the ring, pass B re-walks the slots of pass A
+  int pad_mode, similarity;
+  float eps;
+};
+
+// the (H, W, R, strip width) shapes with a streaming instantiation
+#define NFP_STREAM_SHAPES(X) \
+  X(7, 7, 1, 7)              \
+  X(14, 14, 1, 7)            \
+  X(2, 2, 1, 2)              \
+  X(4, 4, 1, 4)              \
+  X(7, 7, 2, 7)              \
+  X(14, 14, 2, 7)
+
+bool plan_ok_f32(const KParams& P, int mode);
+bool plan_ok_bf16(const KParams& P, int mode);
+int launch_f32(const KParams& P, int mode, const StreamArgs& a, cudaStream_t stream);
+int launch_bf16(const KParams& P, int mode, const StreamArgs& a, cudaStream_t stream);
+
+}  // namespace stream
+}  // namespace nfp

@@ -1,0 +1,827 @@
+// Streaming fused NFP kernels for sm_100a: cosine measure, stride 1, dilation 1, padding = R
+// (the configuration every live model path of the reference uses: models/NFP_Pooling.py:10-16,
+// models/texture_pooling.py:232,302).  Included by nfp_stream_f32.cu / nfp_stream_bf16.cu.
+//
+// One CTA owns one image at a time (persistent loop over b = blockIdx.x, += gridDim.x).  Inside
+// the CTA one PRODUCER warp streams the image's x as chunks of CC channels (CC x H x W contiguous
+// elements of the NCHW tensor) into a shared-memory ring with TMA bulk copies (cp.async.bulk +
+// mbarrier complete_tx); NW CONSUMER warps work on the chunks as they land:
+//
+//   pass A   per-pixel |x_p|^2 and the dot products with the (k*k-1)/2 "forward" window
+//            neighbours (dot(p,q) == dot(q,p): half the window suffices).  A lane owns a TW-pixel
+//            row strip of TWO channels and keeps the strip's accumulators in registers as packed
+//            fp32 pairs (fma.rn.f32x2 -> FFMA2: one issue slot per two FMAs); partial tables are
+//            summed over lanes and warps through shared memory once per image, in a fixed order.
+//   forward  y = dot / (max(|p|,eps) max(|q|,eps)) for the K taps -> the only HBM write;
+//            pooled mode reduces y and x over the plane instead (nfp_pooling head).
+//   backward the table + gy become a per-pixel k x k stencil of coefficients Wd[p][o] (closed form
+//            of ATen's cosine_similarity backward; gather form, no atomics); then
+//   pass B   gx[c][p] = sum_o Wd[p][o] * x[c][p+o], chunk by chunk.  If the whole image fits in
+//            the ring ("resident") the chunks of pass A are still there; otherwise the producer
+//            streams them a second time -- they were read microseconds ago by the same SM, so
+//            the second read is served by the 126 MB L2, not by HBM.  Each warp stages its planes
+//            in shared memory and writes them back with TMA bulk stores.
+//
+// The index arithmetic of the stencil (reflect / replicate / zero padding, tap order of
+// nfp.py:64-67) is evaluated at COMPILE time into __device__ const tables.
+// The (B, C*(k*k-1), H, W) neighbour tensor of the reference (nfp.py:153-154) never exists, x is
+// read from HBM once per kernel, and no cluster / grid synchronisation is needed: images are
+// independent and all resident CTAs have their loads in flight together.
+#pragma once
+
+#include <stdlib.h>
+
+#include <type_traits>
+
+#include "nfp_common.cuh"
+#include "nfp_stream.h"
+
+namespace nfp {
+namespace stream {
+
+template <int H_, int W_, int R_, int TW_>
+struct Cfg {
+  static constexpr int H = H_, W = W_, R = R_, TW = TW_;
+  static constexpr int k = 2 * R + 1, KK = k * k, K = KK - 1, CTR = R * k + R;
+  static constexpr int P = H * W;
+  static constexpr int NSX = W / TW;        // strips per row
+  static constexpr int NS = H * NSX;        // strips per channel plane
+  static constexpr int ND = K / 2;          // forward directions
+  static constexpr int NV = ND + 1;         // table entries per pixel: |x|^2 + ND dots
+  static constexpr int PNV = P * NV;
+  static constexpr int CPW = 32 / NS;       // channels per group (one warp pass)
+  static constexpr int LANES = CPW * NS;    // active lanes
+  static constexpr int XW = (NSX == 1) ? TW : TW + 2 * R;  // loaded columns per row (halo only if strips abut)
+  static constexpr int XOFF = (NSX == 1) ? 0 : R;          // column index of strip pixel 0 inside a loaded row
+  static constexpr int HALO = R * W + R;    // elements a strip may read before / after its channel plane
+  static constexpr bool PACK = (R == 1);    // pass A on packed fp32 pairs (register budget allows it for 3x3)
+  static constexpr int MINB = (R == 1) ? 2 : 1;  // CTAs per SM the register budget is sized for
+  static_assert(W % TW == 0, "strip width must divide W");
+  static_assert(NS <= 32 && CPW >= 1 && (CPW & (CPW - 1)) == 0, "channels per group must be a power of two");
+};
+
+// ---- compile-time stencil tables ----------------------------------------------------------------
+template <class C>
+struct Tables {
+  int16_t fv[C::K * C::P];      // forward: pixel the (padded) tap n of pixel p lands on, -1 = implicit zero
+  int16_t fd[C::K * C::P];      // forward: index into the table of dot(p, fv)
+  int16_t q[C::P * C::KK];      // window pixel p + off(o) when inside the map, else -1
+  uint32_t mask[C::P * C::KK];  // bit n: tap n of pixel p lands on q[p][o]  (o == CTR: on p itself)
+};
+
+constexpr int cmap_index(int i, int n, int mode) {
+  if (i >= 0 && i < n) return i;
+  if (mode == NFPB200_PAD_REFLECT) return i < 0 ? -i : 2 * (n - 1) - i;
+  if (mode == NFPB200_PAD_REPLICATE) return i < 0 ? 0 : n - 1;
+  return -1;
+}
+
+template <class C>
+constexpr Tables<C> make_tables(int mode) {
+  Tables<C> t{};
+  for (int p = 0; p < C::P; ++p)
+    for (int o = 0; o < C::KK; ++o) {
+      const int qr = p / C::W + o / C::k - C::R, qc = p % C::W + o % C::k - C::R;
+      t.q[p * C::KK + o] = (qr >= 0 && qr < C::H && qc >= 0 && qc < C::W) ? (int16_t)(qr * C::W + qc) : (int16_t)-1;
+      t.mask[p * C::KK + o] = 0;
+    }
+  for (int n = 0; n < C::K; ++n) {
+    const int tt = n < (C::K >> 1) ? n : n + 1;  // row-major window with the centre removed (nfp.py:64-67)
+    const int ta = tt / C::k, tb = tt % C::k;
+    for (int p = 0; p < C::P; ++p) {
+      const int pr = p / C::W, pc = p % C::W;
+      const int vr = cmap_index(pr + ta - C::R, C::H, mode), vc = cmap_index(pc + tb - C::R, C::W, mode);
+      if (vr < 0 || vc < 0) {
+        t.fv[n * C::P + p] = -1;
+        t.fd[n * C::P + p] = 0;
+        continue;
+      }
+      const int v = vr * C::W + vc;
+      const int o = (vr - pr + C::R) * C::k + (vc - pc + C::R);
+      t.fv[n * C::P + p] = (int16_t)v;
+      t.fd[n * C::P + p] = (int16_t)(o == C::CTR ? p * C::NV
+                                                 : (o > C::CTR ? p * C::NV + (o - C::CTR) : v * C::NV + (C::CTR - o)));
+      t.mask[p * C::KK + o] |= 1u << n;
+    }
+  }
+  return t;
+}
+
+template <class C, int PADMODE>
+__device__ const Tables<C> g_tables = make_tables<C>(PADMODE);
+
+template <class C>
+const Tables<C>* tables_for(int pad_mode) {
+  const Tables<C>* p = nullptr;
+  cudaError_t e;
+  switch (pad_mode) {
+    case NFPB200_PAD_REFLECT: e = cudaGetSymbolAddress((void**)&p, g_tables<C, NFPB200_PAD_REFLECT>); break;
+    case NFPB200_PAD_REPLICATE: e = cudaGetSymbolAddress((void**)&p, g_tables<C, NFPB200_PAD_REPLICATE>); break;
+    default: e = cudaGetSymbolAddress((void**)&p, g_tables<C, NFPB200_PAD_ZEROS>); break;
+  }
+  return e == cudaSuccess ? p : nullptr;
+}
+
+// ---- PTX helpers: mbarrier, TMA bulk copies, named barriers, packed fp32 ---------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+template <int NTHREADS>
+__device__ __forceinline__ void consumer_sync() {  // named barrier 1: the consumer warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
+}
+
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float sum2(uint64_t v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo + hi;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {  // FFMA2 on sm_100
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// element load from shared memory at a byte address
+template <typename T> __device__ __forceinline__ float ldx(const unsigned char* p);
+template <> __device__ __forceinline__ float ldx<float>(const unsigned char* p) {
+  return *reinterpret_cast<const float*>(p);
+}
+template <> __device__ __forceinline__ float ldx<__nv_bfloat16>(const unsigned char* p) {
+  return __uint_as_float(((uint32_t) * reinterpret_cast<const unsigned short*>(p)) << 16);
+}
+template <typename T> __device__ __forceinline__ void stx(unsigned char* p, float v);
+template <> __device__ __forceinline__ void stx<float>(unsigned char* p, float v) { *reinterpret_cast<float*>(p) = v; }
+template <> __device__ __forceinline__ void stx<__nv_bfloat16>(unsigned char* p, float v) {
+  *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16_rn(v);
+}
+
+constexpr int kMaxStages = 8;
+constexpr int kNW = 8;                  // consumer warps
+constexpr int kSmemPerSM = 227 * 1024;
+constexpr int kLeadPad = 128;           // zeroed bytes in front of the ring (halo reads of the first plane)
+
+__host__ __device__ constexpr int align_up(int n, int a) { return (n + a - 1) / a * a; }
+
+// Shared-memory layout (byte offsets).  Fixed regions first, then a union: the per-warp partial
+// tables of pass A are dead once the image's table is summed, the backward scratch / store staging
+// and the pooled-forward y tile live after that.
+template <typename T, class C, int MODE, int NW>
+struct Smem {
+  static constexpr bool BWD = (MODE == MODE_BWD || MODE == MODE_POOL_BWD);
+  static constexpr int ESZ = (int)sizeof(T);
+  int slot_stride, ring, bars, tfull, inv, tabs, gyraw, uni, total;
+  int t_fv, t_fd, t_q, t_mask;                 // copies of the stencil tables
+  int wtab, rn, selfw, gyS, wd, stg, ytab;     // inside the union
+  int stg_warp;                                // staging bytes per warp (two buffers)
+  __host__ __device__ Smem(int CC, int nst) {
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += (n + 127) & ~127; return r; };
+    // each slot: chunk bytes, then >= HALO zeroed elements (shared with the next slot's "before" halo)
+    slot_stride = align_up(CC * C::P * ESZ + C::HALO * ESZ, 128);
+    o = kLeadPad;
+    ring = take(nst * slot_stride);
+    bars = take((2 * kMaxStages + 4) * 8);
+    tfull = take(C::PNV * 4);
+    inv = take(C::P * 4);
+    tabs = o;
+    if (BWD) {
+      t_q = take(C::P * C::KK * 2);
+      t_mask = take(C::P * C::KK * 4);
+      t_fv = t_fd = 0;
+      gyraw = take(2 * align_up(C::K * C::P * ESZ, 16));
+    } else {
+      t_fv = take(C::K * C::P * 2);
+      t_fd = take(C::K * C::P * 2);
+      t_q = t_mask = 0;
+      gyraw = o;
+    }
+    uni = o;
+    wtab = take(NW * C::CPW * C::PNV * 4);
+    const int u1 = o;
+    o = uni;
+    rn = take(C::P * 4);
+    selfw = take(C::P * 4);
+    gyS = take(C::K * C::P * 4);
+    wd = take(C::P * C::KK * 4);
+    stg_warp = 2 * align_up(2 * C::CPW * C::P * ESZ, 16);
+    stg = take(NW * stg_warp);
+    const int u2 = BWD ? o : uni;
+    o = uni;
+    ytab = take(C::K * C::P * 4);
+    const int u3 = (MODE == MODE_POOL_FWD) ? o : uni;
+    total = u1 > u2 ? (u1 > u3 ? u1 : u3) : (u2 > u3 ? u2 : u3);
+  }
+};
+
+template <typename T, class C, int MODE, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const StreamArgs a, const Tables<C>* __restrict__ gt) {
+  constexpr int W = C::W, R = C::R, TW = C::TW, k = C::k, KK = C::KK, K = C::K, P = C::P;
+  constexpr int NV = C::NV, PNV = C::PNV, NS = C::NS, NSX = C::NSX, CPW = C::CPW, LANES = C::LANES;
+  constexpr int XW = C::XW, XOFF = C::XOFF;
+  constexpr int NT = NW * 32;  // consumer threads
+  constexpr int ESZ = (int)sizeof(T);
+  constexpr bool BWD = (MODE == MODE_BWD || MODE == MODE_POOL_BWD);
+  constexpr bool POOLED = (MODE == MODE_POOL_FWD || MODE == MODE_POOL_BWD);
+  constexpr int GSTRIDE = CPW * P * ESZ;  // bytes between consecutive channel groups
+  constexpr int PSTRIDE = 2 * GSTRIDE;    // one work item = a pair of groups
+  constexpr int GY_BYTES = K * P * ESZ;
+  constexpr int GY_STRIDE = align_up(GY_BYTES, 16);
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int nst = a.nst, NCH = a.NCH, CC = a.CC;
+  const Smem<T, C, MODE, NW> L(CC, nst);
+  unsigned char* ring = smem_raw + L.ring;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* gyfull = empty + kMaxStages;
+  uint64_t* gyempty = gyfull + 2;
+  float* tfull = reinterpret_cast<float*>(smem_raw + L.tfull);
+  float* inv = reinterpret_cast<float*>(smem_raw + L.inv);
+  float* wtab = reinterpret_cast<float*>(smem_raw + L.wtab);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool resident = BWD && a.resident;
+  const uint32_t chunk_bytes = (uint32_t)(CC * P * ESZ);
+
+  if (tid == 0) {
+    for (int s = 0; s < nst; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NW);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&gyfull[s], 1);
+      mbar_init(&gyempty[s], NW);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  // ================================ producer warp ==================================================
+  if (warp == NW) {
+    if (lane == 0) {
+      int slot = 0, img = 0;
+      uint32_t ph = 0;
+      const int npass = (BWD && !resident) ? 2 : 1;
+      for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++img) {
+        if (MODE == MODE_BWD) {
+          const int par = img & 1;
+          mbar_wait(&gyempty[par], ((img >> 1) & 1) ^ 1);
+          mbar_expect_tx(&gyfull[par], (uint32_t)GY_BYTES);
+          bulk_g2s(smem_raw + L.gyraw + par * GY_STRIDE, reinterpret_cast<const T*>(a.gy) + (size_t)b * K * P,
+                   (uint32_t)GY_BYTES, &gyfull[par]);
+        }
+        const unsigned char* xb = reinterpret_cast<const unsigned char*>(a.x) + (size_t)b * a.C * P * ESZ;
+        for (int pass = 0; pass < npass; ++pass) {
+          const unsigned char* src = xb;
+          for (int ch = 0; ch < NCH; ++ch, src += chunk_bytes) {
+            mbar_wait(&empty[slot], ph ^ 1);
+            mbar_expect_tx(&full[slot], chunk_bytes);
+            bulk_g2s(ring + slot * L.slot_stride, src, chunk_bytes, &full[slot]);
+            if (++slot == nst) { slot = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ================================ consumer warps =================================================
+  // prologue (overlaps the first TMA loads): zero the halo pads, copy the stencil tables
+  {
+    uint32_t* z = reinterpret_cast<uint32_t*>(smem_raw);
+    for (int i = tid; i < kLeadPad / 4; i += NT) z[i] = 0u;
+    const int pad_words = (L.slot_stride - (int)chunk_bytes) / 4;
+    for (int s = 0; s < nst; ++s) {
+      uint32_t* zp = reinterpret_cast<uint32_t*>(ring + s * L.slot_stride + chunk_bytes);
+      for (int i = tid; i < pad_words; i += NT) zp[i] = 0u;
+    }
+    if (BWD) {
+      int16_t* dq = reinterpret_cast<int16_t*>(smem_raw + L.t_q);
+      uint32_t* dm = reinterpret_cast<uint32_t*>(smem_raw + L.t_mask);
+      for (int i = tid; i < P * KK; i += NT) {
+        dq[i] = gt->q[i];
+        dm[i] = gt->mask[i];
+      }
+    } else {
+      int16_t* dv = reinterpret_cast<int16_t*>(smem_raw + L.t_fv);
+      int16_t* dd = reinterpret_cast<int16_t*>(smem_raw + L.t_fd);
+      for (int i = tid; i < K * P; i += NT) {
+        dv[i] = gt->fv[i];
+        dd[i] = gt->fd[i];
+      }
+    }
+  }
+  consumer_sync<NT>();
+
+  const float sgn = a.similarity ? 1.f : -1.f;
+  const bool lane_on = lane < LANES;
+  const int chslot = lane_on ? lane / NS : 0;
+  const int pos = lane_on ? lane % NS : 0;
+  const int r = pos / NSX, c0 = (pos % NSX) * TW;
+  const int toff = (chslot * P + r * W + c0) * ESZ;  // byte offset of this lane's strip inside a group
+  const int npairs = CC / (2 * CPW);                 // group pairs per chunk
+  // byte offset of window element (dy, column jj of the loaded row) relative to the strip start
+#define NFP_OFF(dy, jj) (((dy) * W + (jj) - XOFF) * ESZ)
+
+  int slot = 0, img = 0;
+  uint32_t ph = 0;
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++img) {
+    const int slot0 = slot;
+    const uint32_t ph0 = ph;
+
+    // ---- pass A: per-pixel |x|^2 and forward-direction dots, streamed over the chunks -----------
+    {
+      float accs[TW][NV];
+      if constexpr (C::PACK) {
+        uint64_t acc[TW][NV];
+#pragma unroll
+        for (int j = 0; j < TW; ++j)
+#pragma unroll
+          for (int v = 0; v < NV; ++v) acc[j][v] = 0ull;
+        for (int ch = 0; ch < NCH; ++ch) {
+          mbar_wait(&full[slot], ph);
+          const unsigned char* sl = ring + slot * L.slot_stride;
+          if constexpr (MODE == MODE_POOL_FWD) {
+            // GAP(x) of this chunk's channels (NFP_Pooling.py:27): one lane per channel plane; the
+            // job rotates over the warps chunk by chunk
+            const int w0 = (ch * 2) % NW;
+            for (int c = ((warp - w0 + NW) % NW) * 32 + lane; c < CC; c += NT) {
+              const unsigned char* pl = sl + c * P * ESZ;
+              float s = 0.f;
+#pragma unroll 7
+              for (int e = 0; e < P; ++e) s += ldx<T>(pl + e * ESZ);
+              a.gap_x[(size_t)b * a.C + ch * CC + c] = s / (float)P;
+            }
+          }
+          const unsigned char* pa = sl + warp * PSTRIDE + toff;
+          for (int it = warp; it < npairs; it += NW, pa += NW * PSTRIDE) {
+            if (lane_on) {
+              uint64_t xr[R + 1][XW];
+#pragma unroll
+              for (int dy = 0; dy <= R; ++dy)
+#pragma unroll
+                for (int jj = 0; jj < XW; ++jj)
+                  xr[dy][jj] = pack2(ldx<T>(pa + NFP_OFF(dy, jj)), ldx<T>(pa + GSTRIDE + NFP_OFF(dy, jj)));
+#pragma unroll
+              for (int j = 0; j < TW; ++j) {
+                const uint64_t c = xr[0][j + XOFF];
+                acc[j][0] = fma2(c, c, acc[j][0]);
+#pragma unroll
+                for (int dx = 1; dx <= R; ++dx) {
+                  if (j + dx + XOFF < XW) acc[j][dx] = fma2(c, xr[0][j + dx + XOFF], acc[j][dx]);
+                }
+#pragma unroll
+                for (int dy = 1; dy <= R; ++dy)
+#pragma unroll
+                  for (int dx = -R; dx <= R; ++dx) {
+                    if (j + dx + XOFF >= 0 && j + dx + XOFF < XW)
+                      acc[j][dy * k + dx] = fma2(c, xr[dy][j + dx + XOFF], acc[j][dy * k + dx]);
+                  }
+              }
+            }
+          }
+          if (!resident) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+          }
+          if (++slot == nst) { slot = 0; ph ^= 1; }
+        }
+#pragma unroll
+        for (int j = 0; j < TW; ++j)
+#pragma unroll
+          for (int v = 0; v < NV; ++v) accs[j][v] = sum2(acc[j][v]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < TW; ++j)
+#pragma unroll
+          for (int v = 0; v < NV; ++v) accs[j][v] = 0.f;
+        for (int ch = 0; ch < NCH; ++ch) {
+          mbar_wait(&full[slot], ph);
+          const unsigned char* sl = ring + slot * L.slot_stride;
+          if constexpr (MODE == MODE_POOL_FWD) {
+            const int w0 = (ch * 2) % NW;
+            for (int c = ((warp - w0 + NW) % NW) * 32 + lane; c < CC; c += NT) {
+              const unsigned char* pl = sl + c * P * ESZ;
+              float s = 0.f;
+#pragma unroll 7
+              for (int e = 0; e < P; ++e) s += ldx<T>(pl + e * ESZ);
+              a.gap_x[(size_t)b * a.C + ch * CC + c] = s / (float)P;
+            }
+          }
+          const unsigned char* pa = sl + warp * PSTRIDE + toff;
+          for (int it = warp; it < npairs; it += NW, pa += NW * PSTRIDE) {
+            if (lane_on) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const unsigned char* ph_ = pa + h * GSTRIDE;
+                float xr[R + 1][XW];
+#pragma unroll
+                for (int dy = 0; dy <= R; ++dy)
+#pragma unroll
+                  for (int jj = 0; jj < XW; ++jj) xr[dy][jj] = ldx<T>(ph_ + NFP_OFF(dy, jj));
+#pragma unroll
+                for (int j = 0; j < TW; ++j) {
+                  const float c = xr[0][j + XOFF];
+                  accs[j][0] = fmaf(c, c, accs[j][0]);
+#pragma unroll
+                  for (int dx = 1; dx <= R; ++dx) {
+                    if (j + dx + XOFF < XW) accs[j][dx] = fmaf(c, xr[0][j + dx + XOFF], accs[j][dx]);
+                  }
+#pragma unroll
+                  for (int dy = 1; dy <= R; ++dy)
+#pragma unroll
+                    for (int dx = -R; dx <= R; ++dx) {
+                      if (j + dx + XOFF >= 0 && j + dx + XOFF < XW)
+                        accs[j][dy * k + dx] = fmaf(c, xr[dy][j + dx + XOFF], accs[j][dy * k + dx]);
+                    }
+                }
+              }
+            }
+          }
+          if (!resident) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+          }
+          if (++slot == nst) { slot = 0; ph ^= 1; }
+        }
+      }
+      // every active lane publishes its partial sums: table (warp, chslot), entries of strip `pos`
+      if (lane_on) {
+        float* wt = wtab + (warp * CPW + chslot) * PNV + pos * (TW * NV);
+#pragma unroll
+        for (int j = 0; j < TW; ++j)
+#pragma unroll
+          for (int v = 0; v < NV; ++v) wt[j * NV + v] = accs[j][v];
+      }
+    }
+    consumer_sync<NT>();
+    for (int i = tid; i < PNV; i += NT) {
+      float s = 0.f;
+#pragma unroll 8
+      for (int t = 0; t < NW * CPW; ++t) s += wtab[t * PNV + i];  // fixed order: deterministic
+      tfull[i] = s;
+    }
+    consumer_sync<NT>();
+
+    // ---- forward value -----------------------------------------------------------------------------
+    if constexpr (!BWD) {
+      const int16_t* fv = reinterpret_cast<const int16_t*>(smem_raw + L.t_fv);
+      const int16_t* fd = reinterpret_cast<const int16_t*>(smem_raw + L.t_fd);
+      float* ytab = reinterpret_cast<float*>(smem_raw + L.ytab);
+      for (int p = tid; p < P; p += NT) inv[p] = 1.f / fmaxf(sqrtf(tfull[p * NV]), a.eps);
+      consumer_sync<NT>();
+      for (int idx = tid; idx < K * P; idx += NT) {
+        const int p = idx % P;
+        const int v = fv[idx];
+        float yv = 0.f;
+        if (v >= 0) yv = tfull[fd[idx]] * (inv[p] * inv[v]);
+        if (!a.similarity) yv = 1.f - yv;
+        if constexpr (POOLED) {
+          ytab[idx] = yv;
+        } else {
+          reinterpret_cast<T*>(a.y)[(size_t)b * K * P + idx] = from_f32<T>(yv);
+        }
+      }
+      if constexpr (POOLED) {
+        // GAP over the plane of every tap (NFP_Pooling.py:31)
+        consumer_sync<NT>();
+        for (int n = warp; n < K; n += NW) {
+          float s = 0.f;
+          for (int p = lane; p < P; p += 32) s += ytab[n * P + p];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (lane == 0) a.gap_nfp[(size_t)b * K + n] = s / (float)P;
+        }
+      }
+      consumer_sync<NT>();  // tfull / inv / ytab / wtab are rewritten by the next image
+      continue;
+    } else {
+      // ---- backward: stencil coefficients (gather form) ---------------------------------------------
+      const int16_t* qt = reinterpret_cast<const int16_t*>(smem_raw + L.t_q);
+      const uint32_t* mk = reinterpret_cast<const uint32_t*>(smem_raw + L.t_mask);
+      float* rn = reinterpret_cast<float*>(smem_raw + L.rn);
+      float* selfw = reinterpret_cast<float*>(smem_raw + L.selfw);
+      float* gyS = reinterpret_cast<float*>(smem_raw + L.gyS);
+      float* Wd = reinterpret_cast<float*>(smem_raw + L.wd);
+      for (int p = tid; p < P; p += NT) {
+        const float nrm = sqrtf(tfull[p * NV]), N = fmaxf(nrm, a.eps);
+        inv[p] = 1.f / N;
+        rn[p] = nrm > 0.f ? 1.f / (N * nrm) : 0.f;
+      }
+      if constexpr (POOLED) {
+        for (int idx = tid; idx < K * P; idx += NT)
+          gyS[idx] = sgn * a.g_gap_nfp[(size_t)b * K + idx / P] * (1.f / (float)P);
+      } else {
+        const int par = img & 1;
+        mbar_wait(&gyfull[par], (img >> 1) & 1);
+        const unsigned char* g = smem_raw + L.gyraw + par * GY_STRIDE;
+        for (int idx = tid; idx < K * P; idx += NT) gyS[idx] = sgn * ldx<T>(g + idx * ESZ);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&gyempty[par]);
+      }
+      consumer_sync<NT>();
+      // Wd[p][o] = (sum of G over the taps of p that land on q + the taps of q that land on p) / (N_p N_q)
+      for (int idx = tid; idx < P * KK; idx += NT) {
+        const int p = idx / KK, o = idx - p * KK;
+        const int q = (o == C::CTR) ? p : (int)qt[idx];
+        float wv = 0.f;
+        if (q >= 0) {
+          float s = 0.f;
+          uint32_t m = mk[idx];
+          while (m) {
+            const int n = __ffs(m) - 1;
+            m &= m - 1;
+            s += gyS[n * P + p];
+          }
+          if (o != C::CTR) {
+            m = mk[q * KK + (KK - 1 - o)];
+            while (m) {
+              const int n = __ffs(m) - 1;
+              m &= m - 1;
+              s += gyS[n * P + q];
+            }
+            wv = s * (inv[p] * inv[q]);
+          } else {
+            selfw[p] = 2.f * s * (inv[p] * inv[p]);  // taps that land on p itself (replicate padding)
+          }
+        }
+        if (o != C::CTR) Wd[idx] = wv;
+      }
+      consumer_sync<NT>();
+      // centre tap: -(1/(N_p |x_p|)) * sum_o Wd[p][o] dot(p, q_o)   (+ the self pairs)
+      for (int p = tid; p < P; p += NT) {
+        float s = 0.f;
+#pragma unroll
+        for (int o = 0; o < KK; ++o) {
+          if (o == C::CTR) continue;
+          const int q = qt[p * KK + o];
+          if (q >= 0) {
+            const float d = o > C::CTR ? tfull[p * NV + (o - C::CTR)] : tfull[q * NV + (C::CTR - o)];
+            s = fmaf(Wd[p * KK + o], d, s);
+          }
+        }
+        const float sw = selfw[p];
+        Wd[p * KK + C::CTR] = sw - rn[p] * (s + sw * tfull[p * NV]);
+      }
+      consumer_sync<NT>();
+
+      // ---- pass B: gx = stencil(x), chunk by chunk ------------------------------------------------------
+      {
+        unsigned char* mystg = smem_raw + L.stg + warp * L.stg_warp;
+        const int stg_half = L.stg_warp / 2;
+        const float invP = 1.f / (float)P;
+        unsigned char* gxb = reinterpret_cast<unsigned char*>(a.gx) + (size_t)b * a.C * P * ESZ;
+        if (resident) { slot = slot0; ph = ph0; }  // re-walk the slots pass A left in place
+        int nstore = 0;
+        const float* wdp = Wd + (pos * TW) * KK;
+        float wr[(R == 1) ? TW : 1][(R == 1) ? KK : 1];
+        if constexpr (R == 1) {
+#pragma unroll
+          for (int j = 0; j < TW; ++j)
+#pragma unroll
+            for (int o = 0; o < KK; ++o) wr[j][o] = wdp[j * KK + o];
+        }
+        for (int ch = 0; ch < NCH; ++ch) {
+          mbar_wait(&full[slot], ph);
+          const unsigned char* sl = ring + slot * L.slot_stride;
+          const unsigned char* pa = sl + warp * PSTRIDE + toff;
+          for (int it = warp; it < npairs; it += NW, pa += NW * PSTRIDE) {
+            unsigned char* sb = mystg + (nstore & 1) * stg_half;
+            if (nstore >= 2) {
+              if (lane == 0) bulk_wait_read<1>();  // the store that last used this buffer has read it
+              __syncwarp();
+            }
+            if (lane_on) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const unsigned char* ph_ = pa + h * GSTRIDE;
+                float out[TW];
+                float g0 = 0.f;
+                if constexpr (MODE == MODE_POOL_BWD)
+                  g0 = a.g_gap_x[(size_t)b * a.C + ch * CC + (2 * it + h) * CPW + chslot] * invP;
+#pragma unroll
+                for (int j = 0; j < TW; ++j) out[j] = g0;
+                if constexpr (R == 1) {
+#pragma unroll
+                  for (int dy = -R; dy <= R; ++dy) {
+                    float xr[XW];
+#pragma unroll
+                    for (int jj = 0; jj < XW; ++jj) xr[jj] = ldx<T>(ph_ + NFP_OFF(dy, jj));
+#pragma unroll
+                    for (int j = 0; j < TW; ++j)
+#pragma unroll
+                      for (int dx = -R; dx <= R; ++dx) {
+                        if (j + dx + XOFF >= 0 && j + dx + XOFF < XW)
+                          out[j] = fmaf(wr[j][(dy + R) * k + dx + R], xr[j + dx + XOFF], out[j]);
+                      }
+                  }
+                } else {
+                  // wide windows: the coefficients of one window row at a time (register budget)
+#pragma unroll
+                  for (int dy = -R; dy <= R; ++dy) {
+                    float xr[XW], wrow[TW][k];
+#pragma unroll
+                    for (int j = 0; j < TW; ++j)
+#pragma unroll
+                      for (int dx = 0; dx < k; ++dx) wrow[j][dx] = wdp[j * KK + (dy + R) * k + dx];
+#pragma unroll
+                    for (int jj = 0; jj < XW; ++jj) xr[jj] = ldx<T>(ph_ + NFP_OFF(dy, jj));
+#pragma unroll
+                    for (int j = 0; j < TW; ++j)
+#pragma unroll
+                      for (int dx = -R; dx <= R; ++dx) {
+                        if (j + dx + XOFF >= 0 && j + dx + XOFF < XW)
+                          out[j] = fmaf(wrow[j][dx + R], xr[j + dx + XOFF], out[j]);
+                      }
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < TW; ++j) stx<T>(sb + h * GSTRIDE + toff + j * ESZ, out[j]);
+              }
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              // the pair's 2*CPW planes are contiguous in gx
+              bulk_s2g(gxb + ((size_t)ch * CC + (size_t)2 * it * CPW) * P * ESZ, sb, (uint32_t)PSTRIDE);
+              bulk_commit();
+            }
+            ++nstore;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[slot]);
+          if (++slot == nst) { slot = 0; ph ^= 1; }
+        }
+        if (lane == 0) bulk_wait_read<0>();  // staging is part of the union the next image overwrites
+      }
+      consumer_sync<NT>();
+    }
+  }
+  if (BWD && lane == 0) bulk_wait_all();
+#undef NFP_OFF
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+
+struct Plan {
+  bool ok;
+  int CC, NCH, nst, resident, ctas_per_sm;
+  size_t smem;
+};
+
+inline int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+template <typename T, class C, int MODE>
+Plan plan_for(const KParams& P) {
+  Plan pl{false, 0, 0, 0, 0, 0, 0};
+  constexpr int esz = (int)sizeof(T);
+  constexpr bool bwd = (MODE == MODE_BWD || MODE == MODE_POOL_BWD);
+  static const int target_bytes = env_int("NFPB200_CHUNK_BYTES", 16 * 1024);
+  static const int want_ctas = env_int("NFPB200_CTAS_PER_SM", C::MINB);
+  static const int force_stream = env_int("NFPB200_NO_RESIDENT", 0);
+  constexpr int pair = 2 * C::CPW;  // work item: a pair of channel groups
+  if (((size_t)pair * C::P * esz) % 16) return pl;   // TMA bulk store / load granularity
+  if (((size_t)C::K * C::P * esz) % 16) return pl;
+  if (P.C % pair) return pl;
+  // chunk: the largest CC <= target that divides C and is a whole number of group pairs
+  int best = 0;
+  for (int cc = pair; cc <= P.C; cc += pair) {
+    if (P.C % cc) continue;
+    if ((size_t)cc * C::P * esz > (size_t)target_bytes && best) break;
+    best = cc;
+    if ((size_t)cc * C::P * esz >= (size_t)target_bytes) break;
+  }
+  if (!best) return pl;
+  pl.CC = best;
+  pl.NCH = P.C / best;
+  const int max_ctas = want_ctas < 1 ? 1 : (want_ctas > C::MINB ? C::MINB : want_ctas);
+  for (int ctas = max_ctas; ctas >= 1 && !pl.ok; --ctas) {
+    const int budget = kSmemPerSM / ctas - 1024;
+    for (int nst = kMaxStages; nst >= 2; --nst) {  // as many stages as fit: deeper prefetch across images
+      Smem<T, C, MODE, kNW> L(pl.CC, nst);
+      if (L.total > budget) continue;
+      pl.nst = nst;
+      pl.smem = (size_t)L.total;
+      pl.ctas_per_sm = ctas;
+      pl.ok = true;
+      break;
+    }
+  }
+  if (!pl.ok) return pl;
+  pl.resident = (bwd && !force_stream && pl.NCH <= pl.nst) ? 1 : 0;
+  return pl;
+}
+
+template <typename T, class C, int MODE>
+int launch_mode(const KParams& P, StreamArgs a, cudaStream_t stream) {
+  const Plan pl = plan_for<T, C, MODE>(P);
+  if (!pl.ok) return NFPB200_EUNSUPPORTED;
+  a.CC = pl.CC;
+  a.NCH = pl.NCH;
+  a.nst = pl.nst;
+  a.resident = pl.resident;
+  auto kern = stream_kernel<T, C, MODE, kNW>;
+  static const cudaError_t attr_rc =
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerSM);
+  if (attr_rc != cudaSuccess) return (int)attr_rc;
+  static const int num_sms = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  const Tables<C>* gt = tables_for<C>(a.pad_mode);
+  if (!gt) return NFPB200_EINVAL;
+  const int slots = num_sms * pl.ctas_per_sm;
+  const int grid = P.B < slots ? P.B : slots;
+  kern<<<grid, (kNW + 1) * 32, pl.smem, stream>>>(a, gt);
+  return (int)cudaGetLastError();
+}
+
+template <typename T, class C>
+int launch_cfg(const KParams& P, int mode, const StreamArgs& a, cudaStream_t stream) {
+  switch (mode) {
+    case MODE_FWD: return launch_mode<T, C, MODE_FWD>(P, a, stream);
+    case MODE_BWD: return launch_mode<T, C, MODE_BWD>(P, a, stream);
+    case MODE_POOL_FWD: return launch_mode<T, C, MODE_POOL_FWD>(P, a, stream);
+    default: return launch_mode<T, C, MODE_POOL_BWD>(P, a, stream);
+  }
+}
+template <typename T, class C>
+bool plan_ok_cfg(const KParams& P, int mode) {
+  switch (mode) {
+    case MODE_FWD: return plan_for<T, C, MODE_FWD>(P).ok;
+    case MODE_BWD: return plan_for<T, C, MODE_BWD>(P).ok;
+    case MODE_POOL_FWD: return plan_for<T, C, MODE_POOL_FWD>(P).ok;
+    default: return plan_for<T, C, MODE_POOL_BWD>(P).ok;
+  }
+}
+
+template <typename T>
+int launch_dtype(const KParams& P, int mode, const StreamArgs& a, cudaStream_t stream) {
+#define X(H_, W_, R_, TW_) \
+  if (P.H == H_ && P.W == W_ && P.R == R_) return launch_cfg<T, Cfg<H_, W_, R_, TW_>>(P, mode, a, stream);
+  NFP_STREAM_SHAPES(X)
+#undef X
+  return NFPB200_EUNSUPPORTED;
+}
+template <typename T>
+bool plan_ok_dtype(const KParams& P, int mode) {
+#define X(H_, W_, R_, TW_) \
+  if (P.H == H_ && P.W == W_ && P.R == R_) return plan_ok_cfg<T, Cfg<H_, W_, R_, TW_>>(P, mode);
+  NFP_STREAM_SHAPES(X)
+#undef X
+  return false;
+}
+
+}  // namespace stream
+}  // namespace nfp

@@ -93,16 +93,18 @@ def test_random_vs_oracle_generic(measure, geom, cuda_device):
     assert rel_err(gx, gx_ref) < max(tol, 2e-5)
 
 
-FUSED_SHAPES = [(5, 64, 7, 7), (3, 512, 7, 7), (2, 960, 7, 7), (3, 256, 14, 14), (2, 192, 14, 14),
-                (6, 512, 2, 2), (4, 32, 4, 4), (3, 20, 7, 7)]
+FUSED_SHAPES = [(5, 64, 7, 7, 1), (3, 512, 7, 7, 1), (2, 960, 7, 7, 1), (3, 256, 14, 14, 1), (2, 192, 14, 14, 1),
+                (6, 512, 2, 2, 1), (4, 32, 4, 4, 1), (3, 24, 7, 7, 1), (300, 16, 7, 7, 1),
+                (3, 128, 7, 7, 2), (2, 512, 7, 7, 2), (2, 64, 14, 14, 2), (2, 256, 14, 14, 2)]
 
 
-@pytest.mark.parametrize("shape", FUSED_SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("shape", FUSED_SHAPES, ids=lambda s: "x".join(map(str, s[:4])) + f"_r{s[4]}")
 @pytest.mark.parametrize("mode", ["reflect", "zeros", "replicate"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 def test_fused_cosine_vs_oracle(shape, mode, dtype, cuda_device):
-    B, C, H, W = shape
-    gen = torch.Generator().manual_seed(B * 1000 + C + H)
+    B, C, H, W, R = shape
+    K = (2 * R + 1) ** 2 - 1
+    gen = torch.Generator().manual_seed(B * 1000 + C + H + R)
     x = torch.randn(B, C, H, W, generator=gen)
     if C % 3 == 0:
         x = x.relu()
@@ -110,22 +112,37 @@ def test_fused_cosine_vs_oracle(shape, mode, dtype, cuda_device):
     x[-1, :, H - 1, W - 1] *= 1e-9   # ||x|| < eps
     if dtype == torch.bfloat16:
         x = x.bfloat16().float()
-    kw = dict(R=1, measure="cosine", padding=1, padding_mode=mode)
+    kw = dict(R=R, measure="cosine", padding=R, padding_mode=mode)
     cfg = NFPPooling(C, **kw).config
-    if C % 32 == 0:
-        assert NF.describe(shape, dtype, cfg).startswith("fused/"), "shape expected on the fused path"
-    g = torch.randn(B, 8, H, W, generator=gen)
+    assert NF.describe(shape[:4], dtype, cfg).startswith("fused/stream"), "shape expected on the streaming fused path"
+    g = torch.randn(B, K, H, W, generator=gen)
     if dtype == torch.bfloat16:
         g = g.bfloat16().float()
-    y_ref, gx_ref = O.nfp_forward_backward(x.double(), g.double(), **kw)
-    y, gx = _run(x, g, kw, cuda_device, dtype=dtype)
+    if B > 32:   # more images than resident CTAs: exercises the persistent image loop; oracle on a slice
+        sl = slice(B - 4, B)
+        y_ref, gx_ref = O.nfp_forward_backward(x[sl].double(), g[sl].double(), **kw)
+        y, gx = _run(x, g, kw, cuda_device, dtype=dtype)
+        y, gx = y[sl], gx[sl]
+    else:
+        y_ref, gx_ref = O.nfp_forward_backward(x.double(), g.double(), **kw)
+        y, gx = _run(x, g, kw, cuda_device, dtype=dtype)
     tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
     assert rel_err(y, y_ref) < tol
     assert rel_err(gx, gx_ref) < tol
-    if dtype == torch.float32:
-        # and the two CUDA paths agree with each other
+    if dtype == torch.float32 and B <= 32:
+        # and the CUDA paths agree with each other
         y2, gx2 = _run(x, g, kw, cuda_device, path="generic")
         assert rel_err(y, y2) < FP32_TOL and rel_err(gx, gx2) < FP32_TOL
+
+
+def test_fused_is_deterministic(cuda_device):
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(64, 256, 7, 7, generator=gen)
+    g = torch.randn(64, 8, 7, 7, generator=gen)
+    kw = dict(R=1, measure="cosine", padding=1)
+    y1, gx1 = _run(x, g, kw, cuda_device)
+    y2, gx2 = _run(x, g, kw, cuda_device)
+    assert torch.equal(y1, y2) and torch.equal(gx1, gx2)
 
 
 def test_wrapper_golden(cuda_device):
