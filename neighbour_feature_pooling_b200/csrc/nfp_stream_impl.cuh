@@ -61,12 +61,20 @@ struct Cfg {
 };
 
 // ---- compile-time stencil tables ----------------------------------------------------------------
+__host__ __device__ constexpr int align_up(int n, int a) { return (n + a - 1) / a * a; }
+
 template <class C>
 struct Tables {
-  int16_t fv[C::K * C::P];      // forward: pixel the (padded) tap n of pixel p lands on, -1 = implicit zero
-  int16_t fd[C::K * C::P];      // forward: index into the table of dot(p, fv)
-  int16_t q[C::P * C::KK];      // window pixel p + off(o) when inside the map, else -1
-  uint32_t mask[C::P * C::KK];  // bit n: tap n of pixel p lands on q[p][o]  (o == CTR: on p itself)
+  // every array padded to a multiple of 16 bytes: the kernels fetch [fv, fd] (forward) or [q, mask]
+  // (backward) with one TMA bulk copy
+  static constexpr int NF = align_up(C::K * C::P, 8);
+  static constexpr int NQ = align_up(C::P * C::KK, 8);
+  static constexpr int NM = align_up(C::P * C::KK, 4);
+  static constexpr int FWD_BYTES = 2 * NF * 2, BWD_BYTES = NQ * 2 + NM * 4, BWD_OFFSET = FWD_BYTES;
+  alignas(16) int16_t fv[NF];   // forward: pixel the (padded) tap n of pixel p lands on, -1 = implicit zero
+  alignas(16) int16_t fd[NF];   // forward: index into the table of dot(p, fv)
+  alignas(16) int16_t q[NQ];    // window pixel p + off(o) when inside the map, else -1
+  alignas(16) uint32_t mask[NM];  // bit n: tap n of pixel p lands on q[p][o]  (o == CTR: on p itself)
 };
 
 constexpr int cmap_index(int i, int n, int mode) {
@@ -172,6 +180,10 @@ __device__ __forceinline__ void consumer_sync() {  // named barrier 1: the consu
   asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
 }
 
+// programmatic dependent launch (PDL): wait for the preceding grid / let the next grid start launching
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -207,8 +219,6 @@ constexpr int kNW = 8;                  // consumer warps
 constexpr int kSmemPerSM = 227 * 1024;
 constexpr int kLeadPad = 128;           // zeroed bytes in front of the ring (halo reads of the first plane)
 
-__host__ __device__ constexpr int align_up(int n, int a) { return (n + a - 1) / a * a; }
-
 // Shared-memory layout (byte offsets).  Fixed regions first, then a union: the per-warp partial
 // tables of pass A are dead once the image's table is summed, the backward scratch / store staging
 // and the pooled-forward y tile live after that.
@@ -227,18 +237,18 @@ struct Smem {
     slot_stride = align_up(CC * C::P * ESZ + C::HALO * ESZ, 128);
     o = kLeadPad;
     ring = take(nst * slot_stride);
-    bars = take((2 * kMaxStages + 4) * 8);
+    bars = take((2 * kMaxStages + 5) * 8);
     tfull = take(C::PNV * 4);
     inv = take(C::P * 4);
-    tabs = o;
+    tabs = take(BWD ? Tables<C>::BWD_BYTES : Tables<C>::FWD_BYTES);
     if (BWD) {
-      t_q = take(C::P * C::KK * 2);
-      t_mask = take(C::P * C::KK * 4);
+      t_q = tabs;
+      t_mask = tabs + Tables<C>::NQ * 2;
       t_fv = t_fd = 0;
       gyraw = take(2 * align_up(C::K * C::P * ESZ, 16));
     } else {
-      t_fv = take(C::K * C::P * 2);
-      t_fd = take(C::K * C::P * 2);
+      t_fv = tabs;
+      t_fd = tabs + Tables<C>::NF * 2;
       t_q = t_mask = 0;
       gyraw = o;
     }
@@ -282,6 +292,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
   uint64_t* empty = full + kMaxStages;
   uint64_t* gyfull = empty + kMaxStages;
   uint64_t* gyempty = gyfull + 2;
+  uint64_t* tabfull = gyempty + 2;
   float* tfull = reinterpret_cast<float*>(smem_raw + L.tfull);
   float* inv = reinterpret_cast<float*>(smem_raw + L.inv);
   float* wtab = reinterpret_cast<float*>(smem_raw + L.wtab);
@@ -299,6 +310,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
       mbar_init(&gyfull[s], 1);
       mbar_init(&gyempty[s], NW);
     }
+    mbar_init(tabfull, 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -306,6 +318,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
   // ================================ producer warp ==================================================
   if (warp == NW) {
     if (lane == 0) {
+      // the stencil tables are constants: fetch them before waiting for the preceding grid
+      constexpr uint32_t TAB_BYTES = BWD ? Tables<C>::BWD_BYTES : Tables<C>::FWD_BYTES;
+      mbar_expect_tx(tabfull, TAB_BYTES);
+      bulk_g2s(smem_raw + L.tabs, reinterpret_cast<const unsigned char*>(gt) + (BWD ? Tables<C>::BWD_OFFSET : 0),
+               TAB_BYTES, tabfull);
+      grid_launch_dependents();  // PDL: the next grid may be scheduled as SM resources free up
+      grid_dependency_wait();    // PDL: x / gy are produced by the preceding grid
       int slot = 0, img = 0;
       uint32_t ph = 0;
       const int npass = (BWD && !resident) ? 2 : 1;
@@ -333,8 +352,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
   }
 
   // ================================ consumer warps =================================================
-  // prologue (overlaps the first TMA loads): zero the halo pads, copy the stencil tables
-  {
+  // prologue (overlaps the first TMA loads): zero the halo pads.  Pass B multiplies the values read
+  // outside a channel plane by zero coefficients, so they only have to be finite; pass A never
+  // uses the accumulators they feed.
+  if constexpr (BWD) {
     uint32_t* z = reinterpret_cast<uint32_t*>(smem_raw);
     for (int i = tid; i < kLeadPad / 4; i += NT) z[i] = 0u;
     const int pad_words = (L.slot_stride - (int)chunk_bytes) / 4;
@@ -342,22 +363,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
       uint32_t* zp = reinterpret_cast<uint32_t*>(ring + s * L.slot_stride + chunk_bytes);
       for (int i = tid; i < pad_words; i += NT) zp[i] = 0u;
     }
-    if (BWD) {
-      int16_t* dq = reinterpret_cast<int16_t*>(smem_raw + L.t_q);
-      uint32_t* dm = reinterpret_cast<uint32_t*>(smem_raw + L.t_mask);
-      for (int i = tid; i < P * KK; i += NT) {
-        dq[i] = gt->q[i];
-        dm[i] = gt->mask[i];
-      }
-    } else {
-      int16_t* dv = reinterpret_cast<int16_t*>(smem_raw + L.t_fv);
-      int16_t* dd = reinterpret_cast<int16_t*>(smem_raw + L.t_fd);
-      for (int i = tid; i < K * P; i += NT) {
-        dv[i] = gt->fv[i];
-        dd[i] = gt->fd[i];
-      }
-    }
   }
+  grid_dependency_wait();  // PDL: nothing below may touch global memory the preceding grid still uses
   consumer_sync<NT>();
 
   const float sgn = a.similarity ? 1.f : -1.f;
@@ -502,6 +509,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
       }
     }
     consumer_sync<NT>();
+    if (img == 0) mbar_wait(tabfull, 0);  // stencil tables (fetched by the producer at kernel start)
     for (int i = tid; i < PNV; i += NT) {
       float s = 0.f;
 #pragma unroll 8
@@ -783,8 +791,18 @@ int launch_mode(const KParams& P, StreamArgs a, cudaStream_t stream) {
   if (!gt) return NFPB200_EINVAL;
   const int slots = num_sms * pl.ctas_per_sm;
   const int grid = P.B < slots ? P.B : slots;
-  kern<<<grid, (kNW + 1) * 32, pl.smem, stream>>>(a, gt);
-  return (int)cudaGetLastError();
+  static const int use_pdl = env_int("NFPB200_PDL", 1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((kNW + 1) * 32);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  return (int)cudaLaunchKernelEx(&cfg, kern, a, gt);
 }
 
 template <typename T, class C>
