@@ -113,6 +113,12 @@ int nfpb200_abi_version(void);
 /* Human-readable text for a status returned by any entry point (static storage). */
 const char* nfpb200_status_string(int status);
 
+/* Diagnostics: when `device_stamps` is non-null, every fused-kernel CTA records 8 x uint64 nanosecond
+ * timestamps (%globaltimer) of its phase boundaries for its first image at device_stamps[8 * blockIdx.x + k]
+ * (k = 0 consumers ready, 1 pass A done, 2 forward written / coefficients ready, 3 pass B done, 4 stores
+ * drained).  The buffer must hold 8 * (number of CTAs) entries; pass NULL to switch it off.  Not thread-safe. */
+int nfpb200_debug_phase_timing(unsigned long long* device_stamps);
+
 /* (H', W') = Conv2d output size for the descriptor's geometry; validates the descriptor. */
 int nfpb200_output_shape(const nfpb200_desc_t* desc, int32_t* Ho, int32_t* Wo);
 

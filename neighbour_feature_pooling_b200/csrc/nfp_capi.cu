@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "nfp_common.cuh"
+#include "nfp_stream.h"
 
 using namespace nfp;
 
@@ -92,6 +93,11 @@ const char* nfpb200_status_string(int status) {
   }
   if (status > 0) return cudaGetErrorString((cudaError_t)status);
   return "unknown nfpb200 status";
+}
+
+int nfpb200_debug_phase_timing(unsigned long long* device_stamps) {
+  nfp::stream::g_debug_stamps = device_stamps;
+  return NFPB200_OK;
 }
 
 int nfpb200_output_shape(const nfpb200_desc_t* desc, int32_t* Ho, int32_t* Wo) {

@@ -3,6 +3,9 @@
 #include "nfp_stream.h"
 
 namespace nfp {
+namespace stream {
+unsigned long long* g_debug_stamps = nullptr;
+}
 namespace {
 
 bool geometry_ok(const KParams& P, int measure) {
@@ -22,6 +25,7 @@ int op_mode(int op) {
 int run(const KParams& P, int dtype, int mode, stream::StreamArgs a, cudaStream_t s) {
   a.B = P.B; a.C = P.C;
   a.pad_mode = P.mode; a.similarity = P.similarity; a.eps = P.eps;
+  a.dbg = stream::g_debug_stamps;
   return dtype == NFPB200_BF16 ? stream::launch_bf16(P, mode, a, s) : stream::launch_f32(P, mode, a, s);
 }
 

@@ -25,6 +25,7 @@ struct StreamArgs {
   int resident;  // backward: the image fits in the ring, pass B re-walks the slots of pass A
   int pad_mode, similarity;
   float eps;
+  unsigned long long* dbg;  // optional: 8 globaltimer stamps per CTA (first image), see nfpb200_debug_phase_timing
 };
 
 // the (H, W, R, strip width) shapes with a streaming instantiation
@@ -40,6 +41,7 @@ bool plan_ok_f32(const KParams& P, int mode);
 bool plan_ok_bf16(const KParams& P, int mode);
 int launch_f32(const KParams& P, int mode, const StreamArgs& a, cudaStream_t stream);
 int launch_bf16(const KParams& P, int mode, const StreamArgs& a, cudaStream_t stream);
+extern unsigned long long* g_debug_stamps;  // device buffer set through nfpb200_debug_phase_timing (null = off)
 
 }  // namespace stream
 }  // namespace nfp

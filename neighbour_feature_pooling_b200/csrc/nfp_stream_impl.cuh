@@ -184,6 +184,13 @@ __device__ __forceinline__ void consumer_sync() {  // named barrier 1: the consu
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define NFP_STAMP(k) do { if (a.dbg && tid == 0 && img == 0) a.dbg[(size_t)blockIdx.x * 8 + (k)] = globaltimer_ns(); } while (0)
+
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -228,7 +235,8 @@ struct Smem {
   static constexpr int ESZ = (int)sizeof(T);
   int slot_stride, ring, bars, tfull, inv, tabs, gyraw, uni, total;
   int t_fv, t_fd, t_q, t_mask;                 // copies of the stencil tables
-  int wtab, rn, selfw, gyS, wd, stg, ytab;     // inside the union
+  int rn, wd;                                  // backward: 1/(N |x|) per pixel, stencil coefficients
+  int wtab, gyS, stg, ytab;                    // inside the union
   int stg_warp;                                // staging bytes per warp (two buffers)
   __host__ __device__ Smem(int CC, int nst) {
     int o = 0;
@@ -240,6 +248,8 @@ struct Smem {
     bars = take((2 * kMaxStages + 5) * 8);
     tfull = take(C::PNV * 4);
     inv = take(C::P * 4);
+    rn = take(BWD ? C::P * 4 : 0);
+    wd = take(BWD ? C::P * C::KK * 4 : 0);
     tabs = take(BWD ? Tables<C>::BWD_BYTES : Tables<C>::FWD_BYTES);
     if (BWD) {
       t_q = tabs;
@@ -256,10 +266,7 @@ struct Smem {
     wtab = take(NW * C::CPW * C::PNV * 4);
     const int u1 = o;
     o = uni;
-    rn = take(C::P * 4);
-    selfw = take(C::P * 4);
     gyS = take(C::K * C::P * 4);
-    wd = take(C::P * C::KK * 4);
     stg_warp = 2 * align_up(2 * C::CPW * C::P * ESZ, 16);
     stg = take(NW * stg_warp);
     const int u2 = BWD ? o : uni;
@@ -379,9 +386,56 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
 
   int slot = 0, img = 0;
   uint32_t ph = 0;
+  NFP_STAMP(0);  // consumers ready
   for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++img) {
     const int slot0 = slot;
     const uint32_t ph0 = ph;
+
+    // ---- backward, before pass A (overlaps the first chunk loads): the gy-only part of the stencil,
+    // S[p][o] = sum of G over the taps of p that land on q = p + off(o), plus the taps of q that land on p
+    // (o == ctr: the taps of p that land on p itself, replicate padding).  Gather form: no atomics.
+    if constexpr (BWD) {
+      const int16_t* qt = reinterpret_cast<const int16_t*>(smem_raw + L.t_q);
+      const uint32_t* mk = reinterpret_cast<const uint32_t*>(smem_raw + L.t_mask);
+      float* gyS = reinterpret_cast<float*>(smem_raw + L.gyS);
+      float* Wd = reinterpret_cast<float*>(smem_raw + L.wd);
+      if (img == 0) mbar_wait(tabfull, 0);  // stencil tables (fetched by the producer at kernel start)
+      if constexpr (POOLED) {
+        for (int idx = tid; idx < K * P; idx += NT)
+          gyS[idx] = sgn * a.g_gap_nfp[(size_t)b * K + idx / P] * (1.f / (float)P);
+      } else {
+        const int par = img & 1;
+        mbar_wait(&gyfull[par], (img >> 1) & 1);
+        const unsigned char* g = smem_raw + L.gyraw + par * GY_STRIDE;
+        for (int idx = tid; idx < K * P; idx += NT) gyS[idx] = sgn * ldx<T>(g + idx * ESZ);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&gyempty[par]);
+      }
+      consumer_sync<NT>();
+      for (int idx = tid; idx < P * KK; idx += NT) {
+        const int p = idx / KK, o = idx - p * KK;
+        const int q = (o == C::CTR) ? p : (int)qt[idx];
+        float s = 0.f;
+        if (q >= 0) {
+          uint32_t m = mk[idx];
+          while (m) {
+            const int n = __ffs(m) - 1;
+            m &= m - 1;
+            s += gyS[n * P + p];
+          }
+          if (o != C::CTR) {
+            m = mk[q * KK + (KK - 1 - o)];
+            while (m) {
+              const int n = __ffs(m) - 1;
+              m &= m - 1;
+              s += gyS[n * P + q];
+            }
+          }
+        }
+        Wd[idx] = s;
+      }
+      consumer_sync<NT>();  // gyS shares the union with wtab, which the fastest warp writes right after pass A
+    }
 
     // ---- pass A: per-pixel |x|^2 and forward-direction dots, streamed over the chunks -----------
     {
@@ -508,13 +562,22 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
           for (int v = 0; v < NV; ++v) wt[j * NV + v] = accs[j][v];
       }
     }
+    NFP_STAMP(1);  // pass A done (this warp)
     consumer_sync<NT>();
-    if (img == 0) mbar_wait(tabfull, 0);  // stencil tables (fetched by the producer at kernel start)
+    if constexpr (!BWD) {
+      if (img == 0) mbar_wait(tabfull, 0);  // stencil tables (fetched by the producer at kernel start)
+    }
     for (int i = tid; i < PNV; i += NT) {
       float s = 0.f;
 #pragma unroll 8
       for (int t = 0; t < NW * CPW; ++t) s += wtab[t * PNV + i];  // fixed order: deterministic
       tfull[i] = s;
+      if (i % NV == 0) {  // |x_p|^2: the clamped inverse norm (and, backward, the 1/(N |x|) of the norm term)
+        const int p = i / NV;
+        const float nrm = sqrtf(s), N = fmaxf(nrm, a.eps);
+        inv[p] = 1.f / N;
+        if constexpr (BWD) reinterpret_cast<float*>(smem_raw + L.rn)[p] = nrm > 0.f ? 1.f / (N * nrm) : 0.f;
+      }
     }
     consumer_sync<NT>();
 
@@ -523,8 +586,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
       const int16_t* fv = reinterpret_cast<const int16_t*>(smem_raw + L.t_fv);
       const int16_t* fd = reinterpret_cast<const int16_t*>(smem_raw + L.t_fd);
       float* ytab = reinterpret_cast<float*>(smem_raw + L.ytab);
-      for (int p = tid; p < P; p += NT) inv[p] = 1.f / fmaxf(sqrtf(tfull[p * NV]), a.eps);
-      consumer_sync<NT>();
       for (int idx = tid; idx < K * P; idx += NT) {
         const int p = idx % P;
         const int v = fv[idx];
@@ -548,78 +609,36 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
           if (lane == 0) a.gap_nfp[(size_t)b * K + n] = s / (float)P;
         }
       }
+      NFP_STAMP(2);  // forward outputs written
       consumer_sync<NT>();  // tfull / inv / ytab / wtab are rewritten by the next image
       continue;
     } else {
-      // ---- backward: stencil coefficients (gather form) ---------------------------------------------
+      // ---- backward: stencil coefficients.  Wd currently holds S[p][o] (the gy-only part, computed
+      // before pass A); scale by the inverse norms and close the centre tap, one pixel per thread:
+      //   Wd[p][o]   = S[p][o] / (N_p N_q)
+      //   Wd[p][ctr] = sw - (1/(N_p |x_p|)) * (sum_o Wd[p][o] dot(p, q_o) + sw |x_p|^2),  sw = 2 S[p][ctr] / N_p^2
       const int16_t* qt = reinterpret_cast<const int16_t*>(smem_raw + L.t_q);
-      const uint32_t* mk = reinterpret_cast<const uint32_t*>(smem_raw + L.t_mask);
-      float* rn = reinterpret_cast<float*>(smem_raw + L.rn);
-      float* selfw = reinterpret_cast<float*>(smem_raw + L.selfw);
-      float* gyS = reinterpret_cast<float*>(smem_raw + L.gyS);
+      const float* rn = reinterpret_cast<const float*>(smem_raw + L.rn);
       float* Wd = reinterpret_cast<float*>(smem_raw + L.wd);
       for (int p = tid; p < P; p += NT) {
-        const float nrm = sqrtf(tfull[p * NV]), N = fmaxf(nrm, a.eps);
-        inv[p] = 1.f / N;
-        rn[p] = nrm > 0.f ? 1.f / (N * nrm) : 0.f;
-      }
-      if constexpr (POOLED) {
-        for (int idx = tid; idx < K * P; idx += NT)
-          gyS[idx] = sgn * a.g_gap_nfp[(size_t)b * K + idx / P] * (1.f / (float)P);
-      } else {
-        const int par = img & 1;
-        mbar_wait(&gyfull[par], (img >> 1) & 1);
-        const unsigned char* g = smem_raw + L.gyraw + par * GY_STRIDE;
-        for (int idx = tid; idx < K * P; idx += NT) gyS[idx] = sgn * ldx<T>(g + idx * ESZ);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&gyempty[par]);
-      }
-      consumer_sync<NT>();
-      // Wd[p][o] = (sum of G over the taps of p that land on q + the taps of q that land on p) / (N_p N_q)
-      for (int idx = tid; idx < P * KK; idx += NT) {
-        const int p = idx / KK, o = idx - p * KK;
-        const int q = (o == C::CTR) ? p : (int)qt[idx];
-        float wv = 0.f;
-        if (q >= 0) {
-          float s = 0.f;
-          uint32_t m = mk[idx];
-          while (m) {
-            const int n = __ffs(m) - 1;
-            m &= m - 1;
-            s += gyS[n * P + p];
-          }
-          if (o != C::CTR) {
-            m = mk[q * KK + (KK - 1 - o)];
-            while (m) {
-              const int n = __ffs(m) - 1;
-              m &= m - 1;
-              s += gyS[n * P + q];
-            }
-            wv = s * (inv[p] * inv[q]);
-          } else {
-            selfw[p] = 2.f * s * (inv[p] * inv[p]);  // taps that land on p itself (replicate padding)
-          }
-        }
-        if (o != C::CTR) Wd[idx] = wv;
-      }
-      consumer_sync<NT>();
-      // centre tap: -(1/(N_p |x_p|)) * sum_o Wd[p][o] dot(p, q_o)   (+ the self pairs)
-      for (int p = tid; p < P; p += NT) {
+        const float ip = inv[p];
         float s = 0.f;
 #pragma unroll
         for (int o = 0; o < KK; ++o) {
           if (o == C::CTR) continue;
           const int q = qt[p * KK + o];
           if (q >= 0) {
+            const float w = Wd[p * KK + o] * (ip * inv[q]);
             const float d = o > C::CTR ? tfull[p * NV + (o - C::CTR)] : tfull[q * NV + (C::CTR - o)];
-            s = fmaf(Wd[p * KK + o], d, s);
+            Wd[p * KK + o] = w;
+            s = fmaf(w, d, s);
           }
         }
-        const float sw = selfw[p];
+        const float sw = 2.f * Wd[p * KK + C::CTR] * (ip * ip);
         Wd[p * KK + C::CTR] = sw - rn[p] * (s + sw * tfull[p * NV]);
       }
       consumer_sync<NT>();
-
+      NFP_STAMP(2);  // coefficients ready
       // ---- pass B: gx = stencil(x), chunk by chunk ------------------------------------------------------
       {
         unsigned char* mystg = smem_raw + L.stg + warp * L.stg_warp;
@@ -707,12 +726,15 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
           if (lane == 0) mbar_arrive(&empty[slot]);
           if (++slot == nst) { slot = 0; ph ^= 1; }
         }
+        NFP_STAMP(3);  // pass B done (this warp)
         if (lane == 0) bulk_wait_read<0>();  // staging is part of the union the next image overwrites
       }
       consumer_sync<NT>();
     }
   }
   if (BWD && lane == 0) bulk_wait_all();
+  img = 0;
+  NFP_STAMP(4);  // stores drained
 #undef NFP_OFF
 }
 

@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Per-phase timeline of the fused NFP kernels (diagnostic; needs a GPU).
+
+    python tools/phase_timing.py [--shape l4|l3] [--R 1] [--dtype fp32|bf16] [--batch 256]
+
+Uses nfpb200_debug_phase_timing: each CTA stamps %globaltimer at its phase boundaries.  Prints, per
+kernel, the distribution over CTAs of each stamp relative to the earliest CTA start.
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import SHAPES, LayerBench  # noqa: E402
+from neighbour_feature_pooling_b200 import _capi  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--shape", default="l4")
+ap.add_argument("--R", type=int, default=1)
+ap.add_argument("--dtype", default="fp32")
+ap.add_argument("--batch", type=int, default=256)
+args = ap.parse_args()
+C, H, W, _ = SHAPES[args.shape]
+dev = torch.device("cuda:0")
+lb = LayerBench(dev, args.batch, C, H, W, args.R, args.dtype)
+lib = _capi.load()
+stamps = torch.zeros(8 * 1024, dtype=torch.int64, device=dev)
+names = {"fwd": ["ready", "passA", "written"], "bwd": ["ready", "passA", "coef", "passB", "drained"]}
+for which, fn in (("fwd", lb.fwd), ("bwd", lb.bwd)):
+    for i in range(4):
+        fn(i % lb.nbuf)
+    torch.cuda.synchronize()
+    for rep in range(3):
+        stamps.zero_()
+        lib.nfpb200_debug_phase_timing(stamps.data_ptr())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn((rep + 1) % lb.nbuf); e1.record()
+        torch.cuda.synchronize()
+        lib.nfpb200_debug_phase_timing(None)
+        s = stamps.view(-1, 8).cpu()
+        used = s[:, 0] > 0
+        s = s[used].double()
+        t0 = s[:, 0].min()
+        line = f"{which} rep{rep} ctas={int(used.sum())} event_us={e0.elapsed_time(e1) * 1e3:.1f} |"
+        for k, nm in enumerate(names[which]):
+            col = (s[:, k] - t0) / 1e3
+            line += f" {nm}: min {col.min():.1f} med {col.median():.1f} max {col.max():.1f} |"
+        print(line)
