@@ -29,6 +29,7 @@
 // independent and all resident CTAs have their loads in flight together.
 #pragma once
 
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -54,7 +55,7 @@ struct Cfg {
   static constexpr int XW = (NSX == 1) ? TW : TW + 2 * R;  // loaded columns per row (halo only if strips abut)
   static constexpr int XOFF = (NSX == 1) ? 0 : R;          // column index of strip pixel 0 inside a loaded row
   static constexpr int HALO = R * W + R;    // elements a strip may read before / after its channel plane
-  static constexpr bool PACK = (R == 1);    // pass A on packed fp32 pairs (register budget allows it for 3x3)
+  static constexpr bool PACK = (R == 1 && NSX == 1);  // pass A on packed fp32 pairs where the 96-register budget allows it
   static constexpr int MINB = (R == 1) ? 2 : 1;  // CTAs per SM the register budget is sized for
   static_assert(W % TW == 0, "strip width must divide W");
   static_assert(NS <= 32 && CPW >= 1 && (CPW & (CPW - 1)) == 0, "channels per group must be a power of two");
@@ -277,6 +278,8 @@ struct Smem {
   }
 };
 
+// register budget: 9 warps/CTA put up to 3 (1 CTA/SM) or 5 (2 CTAs/SM) warps on one SM sub-partition
+// (16 K registers each) -> at most 96 registers per thread for 2 CTAs/SM, 168 for one
 template <typename T, class C, int MODE, int NW>
 __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const StreamArgs a, const Tables<C>* __restrict__ gt) {
   constexpr int W = C::W, R = C::R, TW = C::TW, k = C::k, KK = C::KK, K = C::K, P = C::P;
@@ -776,8 +779,9 @@ Plan plan_for(const KParams& P) {
   pl.NCH = P.C / best;
   const int max_ctas = want_ctas < 1 ? 1 : (want_ctas > C::MINB ? C::MINB : want_ctas);
   for (int ctas = max_ctas; ctas >= 1 && !pl.ok; --ctas) {
-    const int budget = kSmemPerSM / ctas - 1024;
-    for (int nst = kMaxStages; nst >= 2; --nst) {  // as many stages as fit: deeper prefetch across images
+    const int budget = kSmemPerSM / ctas - 2048;  // the runtime reserves 1 KB per CTA; 1 KB slack
+    static const int max_stages = env_int("NFPB200_MAX_STAGES", kMaxStages);
+    for (int nst = max_stages < kMaxStages ? max_stages : kMaxStages; nst >= 2; --nst) {  // as many stages as fit
       Smem<T, C, MODE, kNW> L(pl.CC, nst);
       if (L.total > budget) continue;
       pl.nst = nst;
@@ -824,7 +828,14 @@ int launch_mode(const KParams& P, StreamArgs a, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  return (int)cudaLaunchKernelEx(&cfg, kern, a, gt);
+  cudaError_t lrc = cudaLaunchKernelEx(&cfg, kern, a, gt);
+  if (lrc != cudaSuccess && getenv("NFPB200_VERBOSE")) {
+    cudaFuncAttributes fa{};
+    cudaFuncGetAttributes(&fa, kern);
+    fprintf(stderr, "[nfpb200] launch failed (%d): grid %d block %d dyn smem %zu static %zu regs %d maxThreads %d\n",
+            (int)lrc, grid, (kNW + 1) * 32, pl.smem, fa.sharedSizeBytes, fa.numRegs, fa.maxThreadsPerBlock);
+  }
+  return (int)lrc;
 }
 
 template <typename T, class C>
