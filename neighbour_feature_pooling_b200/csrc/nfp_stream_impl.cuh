@@ -684,10 +684,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
                     float xr[XW];
 #pragma unroll
                     for (int jj = 0; jj < XW; ++jj) xr[jj] = ldx<T>(ph_ + NFP_OFF(dy, jj));
+                    // dx outer, j inner: consecutive FMAs go to different accumulators (no 4-cycle chains)
 #pragma unroll
-                    for (int j = 0; j < TW; ++j)
+                    for (int dx = -R; dx <= R; ++dx)
 #pragma unroll
-                      for (int dx = -R; dx <= R; ++dx) {
+                      for (int j = 0; j < TW; ++j) {
                         if (j + dx + XOFF >= 0 && j + dx + XOFF < XW)
                           out[j] = fmaf(wr[j][(dy + R) * k + dx + R], xr[j + dx + XOFF], out[j]);
                       }
@@ -704,9 +705,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
 #pragma unroll
                     for (int jj = 0; jj < XW; ++jj) xr[jj] = ldx<T>(ph_ + NFP_OFF(dy, jj));
 #pragma unroll
-                    for (int j = 0; j < TW; ++j)
+                    for (int dx = -R; dx <= R; ++dx)
 #pragma unroll
-                      for (int dx = -R; dx <= R; ++dx) {
+                      for (int j = 0; j < TW; ++j) {
                         if (j + dx + XOFF >= 0 && j + dx + XOFF < XW)
                           out[j] = fmaf(wrow[j][dx + R], xr[j + dx + XOFF], out[j]);
                       }
