@@ -61,6 +61,10 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--no-sweep", action="store_true", help="skip the table over the other configs[1] cases")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the ResNet18+NFP training-step measurement")
+    ap.add_argument("--train-config", default="eurosat", choices=["eurosat", "ucmerced"])
+    ap.add_argument("--train-batch", type=int, default=256, help="images per GPU per training step")
+    ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline budget (seconds of CPU work)")
     return ap.parse_args()
 
@@ -448,6 +452,19 @@ def main():
                                   "path": s.path_bwd})
                     del s
                     torch.cuda.empty_cache()
+    # ---- metric part (ii): ResNet18 + NFP training images/s (DDP over NCCL when N > 1) ---------------------------
+    train = None
+    if not args.no_train:
+        try:
+            import bench_train
+            sampler.tag = "train"
+            train = bench_train.run_gpu(args.train_config, args.train_batch, args.train_steps, 5)
+            sampler.tag = None
+            if rank == 0 and world == 1 and not args.no_cpu_baseline:
+                train["cpu_baseline"] = bench_train.run_cpu_baseline(args.train_config)
+        except Exception as e:  # e.g. torchvision missing: report it, keep the layer numbers
+            sampler.tag = None
+            train = {"unavailable": repr(e)[:300]}
     sampler.stop()
     barrier()
 
@@ -489,6 +506,8 @@ def main():
             line["cpu_baseline"] = cpu
         if sweep:
             line["sweep"] = sweep
+        if train is not None:
+            line["train"] = train
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         try:  # dram bytes per launch from the committed ncu --set full capture of this kernel, if any
             with open(traffic_file) as f:

@@ -1,0 +1,188 @@
+"""End-to-end ResNet18 + NFP training step (BASELINE.json metric part ii: images/s at 1/2/4/8 GPU).
+
+Imported by bench.py (`train` object of the JSON line) and runnable on its own:
+
+    python bench_train.py [--config eurosat|ucmerced] [--batch 256] [--steps 20] [--warmup 5]
+    torchrun --nproc-per-node N bench_train.py ...
+
+The model mirrors the reference's `ResNet18_NFPPooling` (models/texture_pooling.py:153-167): backbone
+`forward_features` -> `nfp_pooling` (this package's drop-in: fused GAP(x), GAP(NFP(x)) kernels) -> `fc`, trained with
+the reference's step (`Lightning_Wrapper.training_step`, lightning_wrappers/Lightning_Wrapper.py:81-105 and :69-79):
+CrossEntropyLoss(label_smoothing=0.05) + Adam(lr).  timm is not installed in this image, so the backbone is
+torchvision's resnet18 with random weights (same architecture; first conv widened for the 13-band EuroSAT input, as timm's
+`in_chans` does).  Data are synthetic.  Multi-GPU = DistributedDataParallel over NCCL, batch-sharded (weak scaling):
+the NFP path itself has no collective; only backbone / nfp_proj / fc gradients are all-reduced.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn as nn  # noqa: E402
+
+CONFIGS = {  # BASELINE.json configs[2] and configs[0]
+    "eurosat": dict(in_chans=13, size=64, classes=10, name="ResNet18+NFP EuroSAT-shaped 13x64x64, 10 classes (layer4 map 512x2x2)"),
+    "ucmerced": dict(in_chans=3, size=224, classes=21, name="ResNet18+NFP UCMerced-shaped 3x224x224, 21 classes (layer4 map 512x7x7)"),
+}
+
+
+class ResNet18Features(nn.Module):
+    """torchvision resnet18 up to layer4 == timm's `forward_features` for resnet18."""
+
+    def __init__(self, in_chans):
+        super().__init__()
+        import torchvision
+        m = torchvision.models.resnet18(weights=None)
+        if in_chans != 3:
+            m.conv1 = nn.Conv2d(in_chans, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.body = nn.Sequential(m.conv1, m.bn1, m.relu, m.maxpool, m.layer1, m.layer2, m.layer3, m.layer4)
+
+    def forward(self, x):
+        return self.body(x)
+
+
+class ResNet18_NFPPooling(nn.Module):
+    """Same composition as the reference class of that name (models/texture_pooling.py:153-167)."""
+
+    def __init__(self, num_classes, in_chans, pool):
+        super().__init__()
+        self.backbone = ResNet18Features(in_chans)
+        self.pool = pool
+        self.fc = nn.Linear(512, num_classes)
+
+    def forward(self, x):
+        return self.fc(self.pool(self.backbone(x)))
+
+
+def make_model(cfg, device, impl="b200"):
+    Params = {"num_ftrs": {"resnet18": 512}, "Model_name": "resnet18", "Dataset": "synthetic",
+              "num_classes": {"synthetic": cfg["classes"]}, "input_size": cfg["size"] // 32}
+    if impl == "b200":
+        import neighbour_feature_pooling_b200 as nfpb
+        pool = nfpb.nfp_pooling(Params=Params)
+    else:  # CPU baseline: the conv-form port of the reference operator inside the reference's wrapper maths
+        from oracle.nfp_convform import ConvFormCosineNFP
+
+        class RefPool(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.nfp_layer = ConvFormCosineNFP(512, R=1, padding=1)
+                self.nfp_proj = nn.Linear(8, 512)
+
+            def forward(self, x):
+                return x.mean((2, 3)) * self.nfp_proj(self.nfp_layer(x).mean((2, 3)))
+        pool = RefPool()
+    return ResNet18_NFPPooling(cfg["classes"], cfg["in_chans"], pool).to(device)
+
+
+def run_gpu(config="eurosat", batch=256, steps=20, warmup=5, amp=True):
+    """Returns a dict (rank 0) with images/s of the DDP training step; uses the current process group if any."""
+    import torch.distributed as dist
+    cfg = CONFIGS[config]
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.manual_seed(1234)
+    model = make_model(cfg, dev).to(memory_format=torch.channels_last)
+    if world > 1:
+        model = nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], gradient_as_bucket_view=True)
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4)
+    crit = nn.CrossEntropyLoss(label_smoothing=0.05)
+    gen = torch.Generator().manual_seed(100 + rank)
+    nhost = 3  # pinned host batches, rotated: every step does its own H2D copy like a DataLoader would
+    hx = [torch.randn(batch, cfg["in_chans"], cfg["size"], cfg["size"], generator=gen).pin_memory() for _ in range(nhost)]
+    hy = [torch.randint(0, cfg["classes"], (batch,), generator=gen).pin_memory() for _ in range(nhost)]
+
+    def step(i):
+        x = hx[i % nhost].to(dev, non_blocking=True).contiguous(memory_format=torch.channels_last)
+        y = hy[i % nhost].to(dev, non_blocking=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            loss = crit(model(x).float(), y)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(warmup):
+        loss = step(i)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier(device_ids=[dev.index])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = step(i)
+    lossv = float(loss.item())  # device->host read of the step's result inside the timed region
+    e1.record()
+    e1.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        tt = torch.tensor([t], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt.item())
+    return {"workload": cfg["name"], "images_per_s": world * steps * batch / t, "ms_per_step": t / steps * 1e3,
+            "batch_per_gpu": batch, "global_batch": batch * world, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "dtype": "bf16 autocast (NFP kernels: bf16 I/O, fp32 accumulate)" if amp else "fp32",
+            "parallelism": f"DDP over NCCL, dp{world}, weak scaling" if world > 1 else "single GPU",
+            "optimizer": "Adam(lr=1e-4), CrossEntropy(label_smoothing=0.05)",
+            "backbone": "torchvision resnet18 (random init; timm absent), channels_last",
+            "h2d_bytes_per_step": hx[0].numel() * 4 + hy[0].numel() * 8, "final_loss": lossv, "data": "synthetic"}
+
+
+def run_cpu_baseline(config="eurosat", batch=8, steps=2):
+    """The reference's CPU path for the same step (conv-form NFP port, fp32), bounded sample."""
+    cfg = CONFIGS[config]
+    torch.manual_seed(1234)
+    model = make_model(cfg, torch.device("cpu"), impl="reference")
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    crit = nn.CrossEntropyLoss(label_smoothing=0.05)
+    x = torch.randn(batch, cfg["in_chans"], cfg["size"], cfg["size"])
+    y = torch.randint(0, cfg["classes"], (batch,))
+
+    def step():
+        loss = crit(model(x), y)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"images_per_s": steps * batch / dt, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} x fwd+bwd+Adam of batch {batch}, fp32, torch {torch.__version__} CPU"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="eurosat", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--fp32", action="store_true")
+    ap.add_argument("--cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    import torch.distributed as dist
+    from neighbour_feature_pooling_b200 import sharding
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    rank, _, world = sharding.init_from_env("nccl", torch.device("cuda", local))
+    out = run_gpu(args.config, args.batch, args.steps, args.warmup, amp=not args.fp32)
+    if rank == 0:
+        if args.cpu_baseline:
+            out["cpu_baseline"] = run_cpu_baseline(args.config)
+        print(json.dumps(out), flush=True)
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

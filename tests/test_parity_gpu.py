@@ -256,3 +256,12 @@ def test_scs_batch_coupling_matches_reference_quirk(cuda_device):
     assert rel_err(y, y_ref) < 1e-4
     y_single = O.nfp_forward(x[:1].double(), **kw)
     assert rel_err(y[:1], y_single) > 1e-3   # genuinely batch-coupled
+
+
+def test_resnet18_nfp_training_step_runs(cuda_device):
+    """bench_train: the reference's model composition on the drop-in trains (loss finite, parameters move)."""
+    import bench_train
+    out = bench_train.run_gpu("eurosat", batch=16, steps=3, warmup=1)
+    assert out["images_per_s"] > 0 and np.isfinite(out["final_loss"])
+    out32 = bench_train.run_gpu("ucmerced", batch=4, steps=2, warmup=1, amp=False)
+    assert np.isfinite(out32["final_loss"])

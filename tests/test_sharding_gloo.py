@@ -66,3 +66,14 @@ def test_two_rank_sharded_pass_equals_single_rank():
         assert p.exitcode == 0
     assert same, "sharded result differs from the single-rank result"
     assert t == 2.0 and n == 5.0
+
+
+def test_train_harness_cpu_reference_arm():
+    """bench_train's CPU baseline model: reference composition (backbone -> GAP(x) * proj(GAP(NFP(x))) -> fc)."""
+    import bench_train
+    cfg = bench_train.CONFIGS["eurosat"]
+    model = bench_train.make_model(cfg, torch.device("cpu"), impl="reference")
+    out = model(torch.randn(2, cfg["in_chans"], cfg["size"], cfg["size"]))
+    assert out.shape == (2, cfg["classes"])
+    r = bench_train.run_cpu_baseline("eurosat", batch=2, steps=1)
+    assert r["images_per_s"] > 0 and r["kind"] == "port"
