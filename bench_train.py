@@ -83,33 +83,92 @@ def make_model(cfg, device, impl="b200"):
     return ResNet18_NFPPooling(cfg["classes"], cfg["in_chans"], pool).to(device)
 
 
-def run_gpu(config="eurosat", batch=256, steps=20, warmup=5, amp=True):
-    """Returns a dict (rank 0) with images/s of the DDP training step; uses the current process group if any."""
+def run_gpu(config="eurosat", batch=256, steps=20, warmup=5, amp=True, use_graph=True):
+    """Returns a dict with images/s of the (DDP) training step; uses the current process group if any.
+
+    The whole step (forward, backward with DDP's bucketed NCCL all-reduce, Adam) is captured in ONE CUDA graph and
+    replayed; if capture fails the eager step is timed instead and the reason is reported."""
     import torch.distributed as dist
     cfg = CONFIGS[config]
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     dev = torch.device("cuda", torch.cuda.current_device())
     torch.manual_seed(1234)
-    model = make_model(cfg, dev).to(memory_format=torch.channels_last)
-    if world > 1:
-        model = nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], gradient_as_bucket_view=True)
-    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4)
+    torch.backends.cudnn.benchmark = True
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev)   # DDP + graph capture: build and warm up on a side stream (PyTorch CUDA-graphs notes)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        model = make_model(cfg, dev).to(memory_format=torch.channels_last)
+        if world > 1:
+            model = nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], gradient_as_bucket_view=True)
+        opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4, capturable=use_graph)
     crit = nn.CrossEntropyLoss(label_smoothing=0.05)
     gen = torch.Generator().manual_seed(100 + rank)
     nhost = 3  # pinned host batches, rotated: every step does its own H2D copy like a DataLoader would
     hx = [torch.randn(batch, cfg["in_chans"], cfg["size"], cfg["size"], generator=gen).pin_memory() for _ in range(nhost)]
     hy = [torch.randint(0, cfg["classes"], (batch,), generator=gen).pin_memory() for _ in range(nhost)]
 
-    def step(i):
-        x = hx[i % nhost].to(dev, non_blocking=True).contiguous(memory_format=torch.channels_last)
-        y = hy[i % nhost].to(dev, non_blocking=True)
+    # input pipeline: the next batch is copied host->device on a copy stream while the current step computes
+    # (what a DataLoader with pin_memory + non_blocking copies does); every step still moves its own batch.
+    copy_stream = torch.cuda.Stream(dev)
+    dx = [torch.empty((batch, cfg["in_chans"], cfg["size"], cfg["size"]), device=dev).contiguous(
+        memory_format=torch.channels_last) for _ in range(2)]
+    dy = [torch.empty((batch,), dtype=torch.long, device=dev) for _ in range(2)]
+    sx, sy = torch.empty_like(dx[0]), torch.empty_like(dy[0])   # static inputs of the captured step
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        b = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])
+            dx[b].copy_(hx[i % nhost], non_blocking=True)
+            dy[b].copy_(hy[i % nhost], non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def train_step(x, y):
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
             loss = crit(model(x).float(), y)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
         return loss
+
+    graph, graph_note, static_loss = None, None, None
+    with torch.cuda.stream(side):
+        sx.copy_(hx[0], non_blocking=True)
+        sy.copy_(hy[0], non_blocking=True)
+        for _ in range(11 if use_graph else 2):   # DDP needs >= 11 eager iterations before capture
+            train_step(sx, sy)
+    main.wait_stream(side)
+    torch.cuda.synchronize(dev)
+    if use_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = train_step(sx, sy)
+            graph.replay()
+            torch.cuda.synchronize(dev)
+        except Exception as e:  # report and fall back to the eager step
+            graph, graph_note = None, repr(e)[:200]
+            torch.cuda.synchronize(dev)
+
+    for e in consumed:
+        e.record(main)
+    prefetch(0)
+
+    def step(i):
+        b = i % 2
+        prefetch(i + 1)
+        main.wait_event(ready[b])
+        sx.copy_(dx[b], non_blocking=True)
+        sy.copy_(dy[b], non_blocking=True)
+        consumed[b].record(main)
+        if graph is not None:
+            graph.replay()
+            return static_loss
+        return train_step(sx, sy)
 
     for i in range(warmup):
         loss = step(i)
@@ -128,13 +187,17 @@ def run_gpu(config="eurosat", batch=256, steps=20, warmup=5, amp=True):
         tt = torch.tensor([t], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t = float(tt.item())
-    return {"workload": cfg["name"], "images_per_s": world * steps * batch / t, "ms_per_step": t / steps * 1e3,
-            "batch_per_gpu": batch, "global_batch": batch * world, "n_gpus": world, "steps": steps, "warmup": warmup,
-            "dtype": "bf16 autocast (NFP kernels: bf16 I/O, fp32 accumulate)" if amp else "fp32",
-            "parallelism": f"DDP over NCCL, dp{world}, weak scaling" if world > 1 else "single GPU",
-            "optimizer": "Adam(lr=1e-4), CrossEntropy(label_smoothing=0.05)",
-            "backbone": "torchvision resnet18 (random init; timm absent), channels_last",
-            "h2d_bytes_per_step": hx[0].numel() * 4 + hy[0].numel() * 8, "final_loss": lossv, "data": "synthetic"}
+    out = {"workload": cfg["name"], "images_per_s": world * steps * batch / t, "ms_per_step": t / steps * 1e3,
+           "batch_per_gpu": batch, "global_batch": batch * world, "n_gpus": world, "steps": steps, "warmup": warmup,
+           "dtype": "bf16 autocast (NFP kernels: bf16 I/O, fp32 accumulate)" if amp else "fp32",
+           "parallelism": f"DDP over NCCL, dp{world}, weak scaling" if world > 1 else "single GPU",
+           "optimizer": "Adam(lr=1e-4), CrossEntropy(label_smoothing=0.05)",
+           "backbone": "torchvision resnet18 (random init; timm absent), channels_last",
+           "cuda_graph": graph is not None,
+           "h2d_bytes_per_step": hx[0].numel() * 4 + hy[0].numel() * 8, "final_loss": lossv, "data": "synthetic"}
+    if graph_note:
+        out["cuda_graph_error"] = graph_note
+    return out
 
 
 def run_cpu_baseline(config="eurosat", batch=8, steps=2):
@@ -169,13 +232,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--fp32", action="store_true")
     ap.add_argument("--cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     import torch.distributed as dist
     from neighbour_feature_pooling_b200 import sharding
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     rank, _, world = sharding.init_from_env("nccl", torch.device("cuda", local))
-    out = run_gpu(args.config, args.batch, args.steps, args.warmup, amp=not args.fp32)
+    out = run_gpu(args.config, args.batch, args.steps, args.warmup, amp=not args.fp32, use_graph=not args.no_graph)
     if rank == 0:
         if args.cpu_baseline:
             out["cpu_baseline"] = run_cpu_baseline(args.config)
