@@ -364,12 +364,33 @@ def run_reference_arm(args, C, H, W, where):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line: keep a private handle on it and point fd 1 at stderr, so that
+    banners printed by libraries (NCCL prints its version on stdout) cannot get in front of the line."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _JSON_OUT
+
+
+def emit(line):
+    out = claim_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     C, H, W, where = SHAPES[args.shape]
     if args.impl == "reference":
         run_reference_arm(args, C, H, W, where)
@@ -520,7 +541,7 @@ def main():
                 line["roofline"]["traffic_source"] = tr[key].get("source")
         except Exception:
             pass
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -234,6 +234,8 @@ def main():
     ap.add_argument("--cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
+    import bench
+    bench.claim_stdout()
     import torch.distributed as dist
     from neighbour_feature_pooling_b200 import sharding
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -243,7 +245,8 @@ def main():
     if rank == 0:
         if args.cpu_baseline:
             out["cpu_baseline"] = run_cpu_baseline(args.config)
-        print(json.dumps(out), flush=True)
+        import bench
+        bench.emit(out)
     if dist.is_initialized():
         dist.destroy_process_group()
 
