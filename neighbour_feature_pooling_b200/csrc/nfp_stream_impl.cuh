@@ -669,16 +669,17 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
               __syncwarp();
             }
             if (lane_on) {
+              if constexpr (R == 1) {
+                // 3x3: all k*k coefficients of the strip live in registers
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const unsigned char* ph_ = pa + h * GSTRIDE;
-                float out[TW];
-                float g0 = 0.f;
-                if constexpr (MODE == MODE_POOL_BWD)
-                  g0 = a.g_gap_x[(size_t)b * a.C + ch * CC + (2 * it + h) * CPW + chslot] * invP;
+                for (int h = 0; h < 2; ++h) {
+                  const unsigned char* ph_ = pa + h * GSTRIDE;
+                  float out[TW];
+                  float g0 = 0.f;
+                  if constexpr (MODE == MODE_POOL_BWD)
+                    g0 = a.g_gap_x[(size_t)b * a.C + ch * CC + (2 * it + h) * CPW + chslot] * invP;
 #pragma unroll
-                for (int j = 0; j < TW; ++j) out[j] = g0;
-                if constexpr (R == 1) {
+                  for (int j = 0; j < TW; ++j) out[j] = g0;
 #pragma unroll
                   for (int dy = -R; dy <= R; ++dy) {
                     float xr[XW];
@@ -693,28 +694,46 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
                           out[j] = fmaf(wr[j][(dy + R) * k + dx + R], xr[j + dx + XOFF], out[j]);
                       }
                   }
-                } else {
-                  // wide windows: the coefficients of one window row at a time (register budget)
 #pragma unroll
-                  for (int dy = -R; dy <= R; ++dy) {
-                    float xr[XW], wrow[TW][k];
+                  for (int j = 0; j < TW; ++j) stx<T>(sb + h * GSTRIDE + toff + j * ESZ, out[j]);
+                }
+              } else {
+                // wider windows: the coefficients of ONE window row at a time (register budget), each row
+                // loaded once and applied to both channel groups of the pair
+                float out[2][TW];
 #pragma unroll
-                    for (int j = 0; j < TW; ++j)
+                for (int h = 0; h < 2; ++h) {
+                  float g0 = 0.f;
+                  if constexpr (MODE == MODE_POOL_BWD)
+                    g0 = a.g_gap_x[(size_t)b * a.C + ch * CC + (2 * it + h) * CPW + chslot] * invP;
 #pragma unroll
-                      for (int dx = 0; dx < k; ++dx) wrow[j][dx] = wdp[j * KK + (dy + R) * k + dx];
+                  for (int j = 0; j < TW; ++j) out[h][j] = g0;
+                }
 #pragma unroll
-                    for (int jj = 0; jj < XW; ++jj) xr[jj] = ldx<T>(ph_ + NFP_OFF(dy, jj));
+                for (int dy = -R; dy <= R; ++dy) {
+                  float wrow[TW][k];
+#pragma unroll
+                  for (int j = 0; j < TW; ++j)
+#pragma unroll
+                    for (int dx = 0; dx < k; ++dx) wrow[j][dx] = wdp[j * KK + (dy + R) * k + dx];
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                    float xr[XW];
+#pragma unroll
+                    for (int jj = 0; jj < XW; ++jj) xr[jj] = ldx<T>(pa + h * GSTRIDE + NFP_OFF(dy, jj));
 #pragma unroll
                     for (int dx = -R; dx <= R; ++dx)
 #pragma unroll
                       for (int j = 0; j < TW; ++j) {
                         if (j + dx + XOFF >= 0 && j + dx + XOFF < XW)
-                          out[j] = fmaf(wrow[j][dx + R], xr[j + dx + XOFF], out[j]);
+                          out[h][j] = fmaf(wrow[j][dx + R], xr[j + dx + XOFF], out[h][j]);
                       }
                   }
                 }
 #pragma unroll
-                for (int j = 0; j < TW; ++j) stx<T>(sb + h * GSTRIDE + toff + j * ESZ, out[j]);
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                  for (int j = 0; j < TW; ++j) stx<T>(sb + h * GSTRIDE + toff + j * ESZ, out[h][j]);
               }
             }
             fence_async_smem();
