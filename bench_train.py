@@ -28,9 +28,11 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 import torch.nn as nn  # noqa: E402
 
-CONFIGS = {  # BASELINE.json configs[2] and configs[0]
-    "eurosat": dict(in_chans=13, size=64, classes=10, name="ResNet18+NFP EuroSAT-shaped 13x64x64, 10 classes (layer4 map 512x2x2)"),
-    "ucmerced": dict(in_chans=3, size=224, classes=21, name="ResNet18+NFP UCMerced-shaped 3x224x224, 21 classes (layer4 map 512x7x7)"),
+CONFIGS = {  # BASELINE.json configs[2] and configs[0]; `raw` = the dtype the dataset's pixels are stored in
+    "eurosat": dict(in_chans=13, size=64, classes=10, raw=torch.int16, raw_max=10000.0,
+                    name="ResNet18+NFP EuroSAT-shaped 13x64x64 (16-bit bands), 10 classes (layer4 map 512x2x2)"),
+    "ucmerced": dict(in_chans=3, size=224, classes=21, raw=torch.uint8, raw_max=255.0,
+                     name="ResNet18+NFP UCMerced-shaped 3x224x224 (8-bit RGB), 21 classes (layer4 map 512x7x7)"),
 }
 
 
@@ -106,14 +108,17 @@ def run_gpu(config="eurosat", batch=256, steps=20, warmup=5, amp=True, use_graph
     crit = nn.CrossEntropyLoss(label_smoothing=0.05)
     gen = torch.Generator().manual_seed(100 + rank)
     nhost = 3  # pinned host batches, rotated: every step does its own H2D copy like a DataLoader would
-    hx = [torch.randn(batch, cfg["in_chans"], cfg["size"], cfg["size"], generator=gen).pin_memory() for _ in range(nhost)]
+    # synthetic batches in the dataset's storage dtype (EuroSAT: 16-bit digital numbers, UCMerced: 8-bit RGB);
+    # normalisation to float happens on the GPU inside the step, as a GPU-side data pipeline would do it
+    hx = [torch.randint(0, int(cfg["raw_max"]), (batch, cfg["in_chans"], cfg["size"], cfg["size"]), generator=gen,
+                        dtype=torch.int32).to(cfg["raw"]).pin_memory() for _ in range(nhost)]
     hy = [torch.randint(0, cfg["classes"], (batch,), generator=gen).pin_memory() for _ in range(nhost)]
+    scale, shift = 2.0 / cfg["raw_max"], -1.0
 
     # input pipeline: the next batch is copied host->device on a copy stream while the current step computes
     # (what a DataLoader with pin_memory + non_blocking copies does); every step still moves its own batch.
     copy_stream = torch.cuda.Stream(dev)
-    dx = [torch.empty((batch, cfg["in_chans"], cfg["size"], cfg["size"]), device=dev).contiguous(
-        memory_format=torch.channels_last) for _ in range(2)]
+    dx = [torch.empty((batch, cfg["in_chans"], cfg["size"], cfg["size"]), device=dev, dtype=cfg["raw"]) for _ in range(2)]
     dy = [torch.empty((batch,), dtype=torch.long, device=dev) for _ in range(2)]
     sx, sy = torch.empty_like(dx[0]), torch.empty_like(dy[0])   # static inputs of the captured step
     ready = [torch.cuda.Event() for _ in range(2)]
@@ -127,7 +132,8 @@ def run_gpu(config="eurosat", batch=256, steps=20, warmup=5, amp=True, use_graph
             dy[b].copy_(hy[i % nhost], non_blocking=True)
             ready[b].record(copy_stream)
 
-    def train_step(x, y):
+    def train_step(xraw, y):
+        x = (xraw.float() * scale + shift).contiguous(memory_format=torch.channels_last)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
             loss = crit(model(x).float(), y)
         opt.zero_grad(set_to_none=True)
@@ -194,7 +200,7 @@ def run_gpu(config="eurosat", batch=256, steps=20, warmup=5, amp=True, use_graph
            "optimizer": "Adam(lr=1e-4), CrossEntropy(label_smoothing=0.05)",
            "backbone": "torchvision resnet18 (random init; timm absent), channels_last",
            "cuda_graph": graph is not None,
-           "h2d_bytes_per_step": hx[0].numel() * 4 + hy[0].numel() * 8, "final_loss": lossv, "data": "synthetic"}
+           "h2d_bytes_per_step": hx[0].numel() * hx[0].element_size() + hy[0].numel() * 8, "final_loss": lossv, "data": "synthetic"}
     if graph_note:
         out["cuda_graph_error"] = graph_note
     return out
