@@ -458,9 +458,11 @@ def main():
     # ---- the other configs[1] cases (reported, not part of `value`) -------------------------------------
     sweep = []
     if not args.no_sweep and rank == 0:
-        for shp in ("l4", "l3"):
-            for r in (1, 2):
-                for dt in ("fp32", "bf16"):
+        cases = [(shp, r, dt) for shp in ("l4", "l3") for r in (1, 2) for dt in ("fp32", "bf16")]
+        cases += [("mbv3", 1, "fp32"), ("vit", 1, "bf16"), ("eurosat", 1, "fp32")]   # configs[3], [4], [2] head maps
+        for shp, r, dt in cases:
+            if True:
+                if True:
                     c, h, w, _ = SHAPES[shp]
                     s = LayerBench(dev, B, c, h, w, r, dt)
                     n = min(args.steps, 200)
