@@ -545,11 +545,17 @@ int launch_t(const KParams& P, const FusedArgs& a0, const Plan& pl, cudaStream_t
   a.S = pl.S;
   a.Cs = pl.Cs;
   auto kern = fused_kernel<T, C, kNW>;
-  // once per instantiation (one process drives one GPU): allow the full 227 KB of dynamic smem
-  static const cudaError_t attr_rc =
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (attr_rc != cudaSuccess) return (int)attr_rc;
-  cudaError_t e;
+  // once per instantiation and device: allow the full 227 KB of dynamic smem
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= 64) return NFPB200_EDEVICE;
+  if (!attr_done[dev]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_done[dev] = true;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(P.B * pl.S));
   cfg.blockDim = dim3(kNW * 32);

@@ -825,14 +825,23 @@ int launch_mode(const KParams& P, StreamArgs a, cudaStream_t stream) {
   a.nst = pl.nst;
   a.resident = pl.resident;
   auto kern = stream_kernel<T, C, MODE, kNW>;
-  static const cudaError_t attr_rc =
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerSM);
-  if (attr_rc != cudaSuccess) return (int)attr_rc;
-  static const int num_sms = [] {
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n;
-  }();
+  // per-device one-time setup (function attributes are per device; a process may drive several GPUs).
+  // Idempotent, so a race between two host threads doing it at once is harmless.
+  constexpr int kMaxDev = 64;
+  static int sm_count[kMaxDev] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= kMaxDev) return NFPB200_EDEVICE;
+  if (sm_count[dev] == 0) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerSM);
+    if (e != cudaSuccess) return (int)e;
+    int n = 0;
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return (int)e;
+    sm_count[dev] = n;
+  }
+  const int num_sms = sm_count[dev];
   const Tables<C>* gt = tables_for<C>(a.pad_mode);
   if (!gt) return NFPB200_EINVAL;
   const int slots = num_sms * pl.ctas_per_sm;
