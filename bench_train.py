@@ -103,7 +103,11 @@ def run_gpu(config="eurosat", batch=256, steps=20, warmup=5, amp=True, use_graph
     with torch.cuda.stream(side):
         model = make_model(cfg, dev).to(memory_format=torch.channels_last)
         if world > 1:
-            model = nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], gradient_as_bucket_view=True)
+            model = nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], gradient_as_bucket_view=True,
+                                                        bucket_cap_mb=int(os.environ.get("NFP_DDP_BUCKET_MB", "25")))
+            if os.environ.get("NFP_DDP_BF16_HOOK", "0") == "1":
+                from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+                model.register_comm_hook(None, default_hooks.bf16_compress_hook)
         opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4, capturable=use_graph)
     crit = nn.CrossEntropyLoss(label_smoothing=0.05)
     gen = torch.Generator().manual_seed(100 + rank)
