@@ -18,8 +18,8 @@
  *
  * Conventions
  *   - plain C types only; every buffer is caller-owned DEVICE memory (NCHW,
- *     contiguous), the library keeps no pointer after a call returns and never
- *     allocates on the hot path;
+ *     contiguous, 16-byte aligned), the library keeps no pointer after a call
+ *     returns and never allocates on the hot path;
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
  *   - return value: 0 on success, a negative NFPB200_E* code for argument
  *     errors, a positive cudaError_t for CUDA failures.  No C++ exception
@@ -86,7 +86,8 @@ enum {
   NFPB200_ESHAPE = -3,       /* kernel window larger than the padded input */
   NFPB200_EWORKSPACE = -4,   /* workspace too small / null */
   NFPB200_EUNSUPPORTED = -5, /* e.g. NFPB200_PATH_FUSED on a problem the fused kernels do not cover */
-  NFPB200_EDEVICE = -6       /* the current device is not sm_100 */
+  NFPB200_EDEVICE = -6,      /* the current device is not sm_100 */
+  NFPB200_EALIGN = -7        /* a tensor pointer is not 16-byte aligned (the fused kernels move data with TMA) */
 };
 
 /* Constructor arguments of NFPPooling (nfp.py:16-18) plus the tensor shape. */

@@ -89,6 +89,7 @@ const char* nfpb200_status_string(int status) {
     case NFPB200_EWORKSPACE: return "workspace missing or too small (see nfpb200_workspace_bytes)";
     case NFPB200_EUNSUPPORTED: return "the fused kernels do not cover this problem (use NFPB200_PATH_AUTO)";
     case NFPB200_EDEVICE: return "current CUDA device is not compute capability 10.x (B200, sm_100a)";
+    case NFPB200_EALIGN: return "tensor pointers must be 16-byte aligned";
     default: break;
   }
   if (status > 0) return cudaGetErrorString((cudaError_t)status);
@@ -145,6 +146,8 @@ int nfpb200_launch_count(const nfpb200_desc_t* desc, int32_t op, int32_t* launch
   return NFPB200_OK;
 }
 
+static inline bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+
 #define NFP_PROLOGUE(OP)                                                                      \
   KParams P;                                                                                  \
   int rc = make_params(desc, &P);                                                             \
@@ -160,6 +163,7 @@ int nfpb200_launch_count(const nfpb200_desc_t* desc, int32_t op, int32_t* launch
 int nfpb200_forward(const nfpb200_desc_t* desc, const void* x, void* y, void* workspace, size_t workspace_bytes,
                     void* stream) {
   if (!x || !y) return NFPB200_EINVAL;
+  if (misaligned(x) || misaligned(y)) return NFPB200_EALIGN;
   NFP_PROLOGUE(NFPB200_OP_FORWARD)
   if (path == 2) return stream_forward(P, desc->dtype, x, y, ctx);
   return path ? fused_forward(P, desc->dtype, x, y, ctx) : generic_forward(P, desc->dtype, desc->measure, x, y, ctx);
@@ -168,6 +172,7 @@ int nfpb200_forward(const nfpb200_desc_t* desc, const void* x, void* y, void* wo
 int nfpb200_backward(const nfpb200_desc_t* desc, const void* x, const void* gy, void* gx, void* workspace,
                      size_t workspace_bytes, void* stream) {
   if (!x || !gy || !gx) return NFPB200_EINVAL;
+  if (misaligned(x) || misaligned(gy) || misaligned(gx)) return NFPB200_EALIGN;
   NFP_PROLOGUE(NFPB200_OP_BACKWARD)
   if (path == 2) return stream_backward(P, desc->dtype, x, gy, gx, ctx);
   return path ? fused_backward(P, desc->dtype, x, gy, gx, ctx)
@@ -177,6 +182,7 @@ int nfpb200_backward(const nfpb200_desc_t* desc, const void* x, const void* gy, 
 int nfpb200_pool_forward(const nfpb200_desc_t* desc, const void* x, float* gap_x, float* gap_nfp, void* workspace,
                          size_t workspace_bytes, void* stream) {
   if (!x || !gap_x || !gap_nfp) return NFPB200_EINVAL;
+  if (misaligned(x)) return NFPB200_EALIGN;
   NFP_PROLOGUE(NFPB200_OP_POOL_FORWARD)
   if (path == 2) return stream_pool_forward(P, desc->dtype, x, gap_x, gap_nfp, ctx);
   return path ? fused_pool_forward(P, desc->dtype, x, gap_x, gap_nfp, ctx)
@@ -186,6 +192,7 @@ int nfpb200_pool_forward(const nfpb200_desc_t* desc, const void* x, float* gap_x
 int nfpb200_pool_backward(const nfpb200_desc_t* desc, const void* x, const float* g_gap_x, const float* g_gap_nfp,
                           void* gx, void* workspace, size_t workspace_bytes, void* stream) {
   if (!x || !g_gap_x || !g_gap_nfp || !gx) return NFPB200_EINVAL;
+  if (misaligned(x) || misaligned(gx)) return NFPB200_EALIGN;
   NFP_PROLOGUE(NFPB200_OP_POOL_BACKWARD)
   if (path == 2) return stream_pool_backward(P, desc->dtype, x, g_gap_x, g_gap_nfp, gx, ctx);
   return path ? fused_pool_backward(P, desc->dtype, x, g_gap_x, g_gap_nfp, gx, ctx)

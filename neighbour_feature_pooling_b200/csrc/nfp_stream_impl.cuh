@@ -58,6 +58,7 @@ struct Cfg {
   static constexpr bool PACK = (R == 1 && NSX == 1);  // pass A on packed fp32 pairs where the 96-register budget allows it
   static constexpr int MINB = (R == 1) ? 2 : 1;  // CTAs per SM the register budget is sized for
   static_assert(W % TW == 0, "strip width must divide W");
+  static_assert(HALO * 4 <= 128, "the zeroed lead pad in front of the ring must cover the halo");
   static_assert(NS <= 32 && CPW >= 1 && (CPW & (CPW - 1)) == 0, "channels per group must be a power of two");
 };
 

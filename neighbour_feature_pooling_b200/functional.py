@@ -109,7 +109,10 @@ def _prepare(x: torch.Tensor):
         raise RuntimeError("NFP kernels compute in fp32; float64 inputs are not supported")
     if x.dtype not in _KERNEL_DTYPES:  # fp16: widen, the kernels accumulate in fp32 anyway
         x = x.float()
-    return x.contiguous(), out_dtype
+    x = x.contiguous()
+    if x.data_ptr() % 16:   # a view at an odd storage offset: the kernels move data with 16-byte TMA copies
+        x = x.clone()
+    return x, out_dtype
 
 
 def _desc_for(x: torch.Tensor, cfg: NFPConfig) -> _capi.Desc:
@@ -152,6 +155,8 @@ class _NFPSimilarity(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         desc = _desc_for(x, ctx.cfg)
         gy = gy.to(x.dtype).contiguous()
+        if gy.data_ptr() % 16:
+            gy = gy.clone()
         gx = torch.empty_like(x)
         with torch.cuda.device(x.device):
             ws, ws_ptr, ws_n = _workspace(desc, _capi.OP_BACKWARD, x.device)

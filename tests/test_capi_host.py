@@ -60,6 +60,9 @@ def test_argument_errors():
     assert lib.nfpb200_output_shape(ctypes.byref(d), ctypes.byref(ho), ctypes.byref(wo)) == -1
     # null data pointers are rejected before anything touches the device
     assert lib.nfpb200_forward(ctypes.byref(_desc()), None, None, None, 0, None) == -1
+    # misaligned tensor pointers are refused before any launch (the fused kernels use 16-byte TMA copies)
+    assert lib.nfpb200_forward(ctypes.byref(_desc()), 0x1004, 0x2000, None, 0, None) == -7
+    assert "16-byte" in _capi.status_string(-7)
     with pytest.raises(RuntimeError, match="invalid argument"):
         _capi.check(-1, "x")
 

@@ -279,6 +279,11 @@ def test_autocast_and_no_grad(cuda_device):
     assert xh.grad.dtype == torch.float16
     with pytest.raises(RuntimeError, match="float64"):
         layer(x.double())
+    # a view at an odd storage offset (data pointer not 16-byte aligned) is accepted
+    big = torch.randn(2 * 64 * 49 + 1, device=cuda_device)
+    xo = big[1:].view(2, 64, 7, 7)
+    assert xo.data_ptr() % 16 != 0
+    assert rel_err(layer(xo).cpu(), layer(xo.clone()).cpu()) == 0.0
     # non-contiguous (channels_last) input is accepted
     xc = x.to(memory_format=torch.channels_last)
     assert rel_err(layer(xc).cpu(), layer(x).cpu()) == 0.0
