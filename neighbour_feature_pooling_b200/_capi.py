@@ -11,7 +11,9 @@ import math
 import os
 import threading
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnfp_b200.so")
+# NFPB200_LIB selects another BUILD of the same native library (kernel A/B experiments: `build.py --variant`)
+_LIB_PATH = os.environ.get("NFPB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
+                                                          "libnfp_b200.so")
 
 ABI_VERSION = 1
 

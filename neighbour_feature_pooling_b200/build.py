@@ -44,16 +44,23 @@ def needs_build() -> bool:
     return not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < _deps()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines=()) -> str:
+    """variant / defines: an experimental build `lib/libnfp_b200.<variant>.so` compiled with extra -D flags
+    (selected at run time with NFPB200_LIB=<path>); the default build is what ships."""
+    lib_path, obj_dir = LIB_PATH, OBJ_DIR
+    if variant:
+        lib_path = os.path.join(LIB_DIR, f"libnfp_b200.{variant}.so")
+        obj_dir = os.path.join(OBJ_DIR, variant)
+    elif not force and not needs_build():
         return LIB_PATH
     nvcc = _nvcc()
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
+    flags = [*NVCC_FLAGS, *[f"-D{d}" for d in defines]]
 
     def compile_one(src):
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         with open(obj + ".ptxas.log", "w") as f:
             f.write(r.stdout + r.stderr)
@@ -65,14 +72,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    tmp = LIB_PATH + ".tmp"
+    tmp = lib_path + ".tmp"
     r = subprocess.run([nvcc, "-shared", "--cudart", "static", "-o", tmp, *objs], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    os.replace(tmp, LIB_PATH)
-    return LIB_PATH
+    os.replace(tmp, lib_path)
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=variant,
+                 defines=[a[2:] for a in sys.argv if a.startswith("-D")])
     print(path)

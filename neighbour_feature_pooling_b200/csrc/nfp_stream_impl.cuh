@@ -37,6 +37,11 @@
 #include "nfp_common.cuh"
 #include "nfp_stream.h"
 
+// pass B on packed fp32 pairs (FFMA2 with scalar-broadcast coefficients) vs scalar FFMA: A/B switch
+#ifndef NFP_PASSB_FFMA2
+#define NFP_PASSB_FFMA2 1
+#endif
+
 namespace nfp {
 namespace stream {
 
@@ -65,18 +70,38 @@ struct Cfg {
 // ---- compile-time stencil tables ----------------------------------------------------------------
 __host__ __device__ constexpr int align_up(int n, int a) { return (n + a - 1) / a * a; }
 
+// taps that point outside the map (they fold back onto a window pixel under reflect / replicate padding)
+template <class C>
+constexpr int count_outside_taps() {
+  int n = 0;
+  for (int p = 0; p < C::P; ++p)
+    for (int o = 0; o < C::KK; ++o) {
+      if (o == C::CTR) continue;
+      const int qr = p / C::W + o / C::k - C::R, qc = p % C::W + o % C::k - C::R;
+      if (qr < 0 || qr >= C::H || qc < 0 || qc >= C::W) ++n;
+    }
+  return n;
+}
+
 template <class C>
 struct Tables {
-  // every array padded to a multiple of 16 bytes: the kernels fetch [fv, fd] (forward) or [q, mask]
+  // every array padded to a multiple of 16 bytes: the kernels fetch [fv, fd] (forward) or [q, fsrc, fdst, fptr]
   // (backward) with one TMA bulk copy
   static constexpr int NF = align_up(C::K * C::P, 8);
   static constexpr int NQ = align_up(C::P * C::KK, 8);
-  static constexpr int NM = align_up(C::P * C::KK, 4);
-  static constexpr int FWD_BYTES = 2 * NF * 2, BWD_BYTES = NQ * 2 + NM * 4, BWD_OFFSET = FWD_BYTES;
+  static constexpr int NOUT = count_outside_taps<C>();
+  static constexpr int NFS = align_up(NOUT + 1, 8);
+  static constexpr int NFP = align_up(NOUT + 2, 8);
+  static constexpr int FWD_BYTES = 2 * NF * 2, BWD_BYTES = (NQ + 2 * NFS + NFP) * 2, BWD_OFFSET = FWD_BYTES;
   alignas(16) int16_t fv[NF];   // forward: pixel the (padded) tap n of pixel p lands on, -1 = implicit zero
   alignas(16) int16_t fd[NF];   // forward: index into the table of dot(p, fv)
   alignas(16) int16_t q[NQ];    // window pixel p + off(o) when inside the map, else -1
-  alignas(16) uint32_t mask[NM];  // bit n: tap n of pixel p lands on q[p][o]  (o == CTR: on p itself)
+  // backward, folded taps in CSR form: window entry fdst[i] = p*KK + o of a border pixel p additionally receives
+  // the upstream gradient elements fsrc[fptr[i] .. fptr[i+1]) (flat n*P + p) of p's taps that point outside the
+  // map and are folded onto p + off(o) by the padding (o == CTR: onto p itself); fptr[NFP-1] = number of entries
+  alignas(16) int16_t fsrc[NFS];
+  alignas(16) int16_t fdst[NFS];
+  alignas(16) int16_t fptr[NFP];
 };
 
 constexpr int cmap_index(int i, int n, int mode) {
@@ -93,7 +118,6 @@ constexpr Tables<C> make_tables(int mode) {
     for (int o = 0; o < C::KK; ++o) {
       const int qr = p / C::W + o / C::k - C::R, qc = p % C::W + o % C::k - C::R;
       t.q[p * C::KK + o] = (qr >= 0 && qr < C::H && qc >= 0 && qc < C::W) ? (int16_t)(qr * C::W + qc) : (int16_t)-1;
-      t.mask[p * C::KK + o] = 0;
     }
   for (int n = 0; n < C::K; ++n) {
     const int tt = n < (C::K >> 1) ? n : n + 1;  // row-major window with the centre removed (nfp.py:64-67)
@@ -111,9 +135,39 @@ constexpr Tables<C> make_tables(int mode) {
       t.fv[n * C::P + p] = (int16_t)v;
       t.fd[n * C::P + p] = (int16_t)(o == C::CTR ? p * C::NV
                                                  : (o > C::CTR ? p * C::NV + (o - C::CTR) : v * C::NV + (C::CTR - o)));
-      t.mask[p * C::KK + o] |= 1u << n;
     }
   }
+  // folded taps, grouped by the window entry they land on (border pixels only)
+  int nfd = 0, nfs = 0;
+  for (int p = 0; p < C::P; ++p) {
+    const int pr = p / C::W, pc = p % C::W;
+    if (pr >= C::R && pr < C::H - C::R && pc >= C::R && pc < C::W - C::R) continue;  // no tap leaves the map
+    int land[C::K] = {};  // window entry the outside tap n folds onto, -1 = none
+    for (int n = 0; n < C::K; ++n) {
+      const int tt = n < (C::K >> 1) ? n : n + 1;
+      const int rr = pr + tt / C::k - C::R, cc = pc + tt % C::k - C::R;
+      land[n] = -1;
+      if (rr >= 0 && rr < C::H && cc >= 0 && cc < C::W) continue;  // a direct tap
+      const int vr = cmap_index(rr, C::H, mode), vc = cmap_index(cc, C::W, mode);
+      if (vr < 0 || vc < 0) continue;  // zero padding
+      land[n] = (vr - pr + C::R) * C::k + (vc - pc + C::R);
+    }
+    for (int o = 0; o < C::KK; ++o) {
+      int cnt = 0;
+      for (int n = 0; n < C::K; ++n)
+        if (land[n] == o) {
+          if (cnt == 0) {
+            t.fdst[nfd] = (int16_t)(p * C::KK + o);
+            t.fptr[nfd] = (int16_t)nfs;
+          }
+          t.fsrc[nfs++] = (int16_t)(n * C::P + p);
+          ++cnt;
+        }
+      if (cnt) ++nfd;
+    }
+  }
+  t.fptr[nfd] = (int16_t)nfs;
+  t.fptr[Tables<C>::NFP - 1] = (int16_t)nfd;
   return t;
 }
 
@@ -203,6 +257,9 @@ __device__ __forceinline__ float sum2(uint64_t v) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
   return lo + hi;
 }
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {  // FFMA2 on sm_100
   uint64_t d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
@@ -224,6 +281,11 @@ template <> __device__ __forceinline__ void stx<__nv_bfloat16>(unsigned char* p,
 }
 
 constexpr int kMaxStages = 8;
+// warps of a CTA: NW consumers and one producer (TMA issue)
+__host__ __device__ constexpr int block_threads(int mode, int nw) {
+  (void)mode;
+  return (nw + 1) * 32;
+}
 constexpr int kNW = 8;                  // consumer warps
 constexpr int kSmemPerSM = 227 * 1024;
 constexpr int kLeadPad = 128;           // zeroed bytes in front of the ring (halo reads of the first plane)
@@ -235,54 +297,60 @@ template <typename T, class C, int MODE, int NW>
 struct Smem {
   static constexpr bool BWD = (MODE == MODE_BWD || MODE == MODE_POOL_BWD);
   static constexpr int ESZ = (int)sizeof(T);
-  int slot_stride, ring, bars, tfull, inv, tabs, gyraw, uni, total;
-  int t_fv, t_fd, t_q, t_mask;                 // copies of the stencil tables
-  int rn, wd;                                  // backward: 1/(N |x|) per pixel, stencil coefficients
-  int wtab, gyS, stg, ytab;                    // inside the union
+  int slot_stride, lead, ring, bars, tfull, inv, tabs, gyraw, uni, total;
+  int t_fv, t_fd, t_q, t_fsrc, t_fdst, t_fptr;  // copies of the stencil tables
+  int rn, wd, gp;                              // backward: 1/(N |x|) per pixel, stencil coefficients, stencil-warp scratch
+  int wtab, stg, ytab;                         // inside the union
   int stg_warp;                                // staging bytes per warp (two buffers)
   __host__ __device__ Smem(int CC, int nst) {
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 127) & ~127; return r; };
-    // each slot: chunk bytes, then >= HALO zeroed elements (shared with the next slot's "before" halo)
-    slot_stride = align_up(CC * C::P * ESZ + C::HALO * ESZ, 128);
-    o = kLeadPad;
-    ring = take(nst * slot_stride);
-    bars = take((2 * kMaxStages + 5) * 8);
+    // everything whose size is known at compile time comes first (so its address is a constant in the
+    // kernel); the ring, whose geometry depends on the run-time chunk size and stage count, comes last
+    bars = take((2 * kMaxStages + 8) * 8);
     tfull = take(C::PNV * 4);
     inv = take(C::P * 4);
     rn = take(BWD ? C::P * 4 : 0);
     wd = take(BWD ? C::P * C::KK * 4 : 0);
+    gp = take(BWD ? C::P * C::KK * 4 : 0);
     tabs = take(BWD ? Tables<C>::BWD_BYTES : Tables<C>::FWD_BYTES);
     if (BWD) {
       t_q = tabs;
-      t_mask = tabs + Tables<C>::NQ * 2;
+      t_fsrc = t_q + Tables<C>::NQ * 2;
+      t_fdst = t_fsrc + Tables<C>::NFS * 2;
+      t_fptr = t_fdst + Tables<C>::NFS * 2;
       t_fv = t_fd = 0;
       gyraw = take(2 * align_up(C::K * C::P * ESZ, 16));
     } else {
       t_fv = tabs;
       t_fd = tabs + Tables<C>::NF * 2;
-      t_q = t_mask = 0;
+      t_q = t_fsrc = t_fdst = t_fptr = 0;
       gyraw = o;
     }
     uni = o;
     wtab = take(NW * C::CPW * C::PNV * 4);
     const int u1 = o;
     o = uni;
-    gyS = take(C::K * C::P * 4);
     stg_warp = 2 * align_up(2 * C::CPW * C::P * ESZ, 16);
     stg = take(NW * stg_warp);
     const int u2 = BWD ? o : uni;
     o = uni;
     ytab = take(C::K * C::P * 4);
     const int u3 = (MODE == MODE_POOL_FWD) ? o : uni;
-    total = u1 > u2 ? (u1 > u3 ? u1 : u3) : (u2 > u3 ? u2 : u3);
+    o = u1 > u2 ? (u1 > u3 ? u1 : u3) : (u2 > u3 ? u2 : u3);
+    // each slot: chunk bytes, then >= HALO zeroed elements (shared with the next slot's "before" halo);
+    // kLeadPad zeroed bytes in front of the first slot
+    slot_stride = align_up(CC * C::P * ESZ + C::HALO * ESZ, 128);
+    lead = take(kLeadPad);
+    ring = take(nst * slot_stride);
+    total = o;
   }
 };
 
 // register budget: 9 warps/CTA put up to 3 (1 CTA/SM) or 5 (2 CTAs/SM) warps on one SM sub-partition
 // (16 K registers each) -> at most 96 registers per thread for 2 CTAs/SM, 168 for one
 template <typename T, class C, int MODE, int NW>
-__global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const StreamArgs a, const Tables<C>* __restrict__ gt) {
+__global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kernel(const StreamArgs a, const Tables<C>* __restrict__ gt) {
   constexpr int W = C::W, R = C::R, TW = C::TW, k = C::k, KK = C::KK, K = C::K, P = C::P;
   constexpr int NV = C::NV, PNV = C::PNV, NS = C::NS, NSX = C::NSX, CPW = C::CPW, LANES = C::LANES;
   constexpr int XW = C::XW, XOFF = C::XOFF;
@@ -308,7 +376,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
   float* inv = reinterpret_cast<float*>(smem_raw + L.inv);
   float* wtab = reinterpret_cast<float*>(smem_raw + L.wtab);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index through a shuffle: tells the compiler it is warp-uniform (uniform registers / datapath for the
+  // per-warp address arithmetic)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const bool resident = BWD && a.resident;
   const uint32_t chunk_bytes = (uint32_t)(CC * P * ESZ);
 
@@ -319,7 +389,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&gyfull[s], 1);
-      mbar_init(&gyempty[s], NW);
+      mbar_init(&gyempty[s], 1);
     }
     mbar_init(tabfull, 1);
     fence_mbar_init();
@@ -367,7 +437,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
   // outside a channel plane by zero coefficients, so they only have to be finite; pass A never
   // uses the accumulators they feed.
   if constexpr (BWD) {
-    uint32_t* z = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* z = reinterpret_cast<uint32_t*>(smem_raw + L.lead);
     for (int i = tid; i < kLeadPad / 4; i += NT) z[i] = 0u;
     const int pad_words = (L.slot_stride - (int)chunk_bytes) / 4;
     for (int s = 0; s < nst; ++s) {
@@ -395,50 +465,59 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
     const int slot0 = slot;
     const uint32_t ph0 = ph;
 
-    // ---- backward, before pass A (overlaps the first chunk loads): the gy-only part of the stencil,
-    // S[p][o] = sum of G over the taps of p that land on q = p + off(o), plus the taps of q that land on p
-    // (o == ctr: the taps of p that land on p itself, replicate padding).  Gather form: no atomics.
+    // ---- backward, before pass A (overlaps the latency of the first chunk loads): the gy-only part of the
+    // stencil, S[p][o] = sum of G over the taps of p that land on q = p + off(o), plus the taps of q that land on p
+    // (o == ctr: the taps of p that land on p itself, replicate padding).  Gather form: no atomics, fixed order.
     if constexpr (BWD) {
       const int16_t* qt = reinterpret_cast<const int16_t*>(smem_raw + L.t_q);
-      const uint32_t* mk = reinterpret_cast<const uint32_t*>(smem_raw + L.t_mask);
-      float* gyS = reinterpret_cast<float*>(smem_raw + L.gyS);
+      const int16_t* fsrc = reinterpret_cast<const int16_t*>(smem_raw + L.t_fsrc);
+      const int16_t* fdst = reinterpret_cast<const int16_t*>(smem_raw + L.t_fdst);
+      const int16_t* fptr = reinterpret_cast<const int16_t*>(smem_raw + L.t_fptr);
       float* Wd = reinterpret_cast<float*>(smem_raw + L.wd);
+      float* Gp = reinterpret_cast<float*>(smem_raw + L.gp);
       if (img == 0) mbar_wait(tabfull, 0);  // stencil tables (fetched by the producer at kernel start)
+      const int par = img & 1;
+      const unsigned char* g = smem_raw + L.gyraw + par * GY_STRIDE;
       if constexpr (POOLED) {
-        for (int idx = tid; idx < K * P; idx += NT)
-          gyS[idx] = sgn * a.g_gap_nfp[(size_t)b * K + idx / P] * (1.f / (float)P);
+        // d GAP(y) / dy: the same value on every pixel of a tap plane
+        if (tid < K) reinterpret_cast<float*>(smem_raw + L.gyraw)[tid] = a.g_gap_nfp[(size_t)b * K + tid] * (1.f / (float)P);
+        consumer_sync<NT>();
       } else {
-        const int par = img & 1;
         mbar_wait(&gyfull[par], (img >> 1) & 1);
-        const unsigned char* g = smem_raw + L.gyraw + par * GY_STRIDE;
-        for (int idx = tid; idx < K * P; idx += NT) gyS[idx] = sgn * ldx<T>(g + idx * ESZ);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&gyempty[par]);
       }
-      consumer_sync<NT>();
+      auto G = [&](int flat) -> float {  // upstream gradient element n*P + p
+        if constexpr (POOLED) return reinterpret_cast<const float*>(smem_raw + L.gyraw)[flat / P];
+        else return ldx<T>(g + flat * ESZ);
+      };
+      // G'[p][o] = gradient of the taps of p that land on p + off(o): the direct tap ...
       for (int idx = tid; idx < P * KK; idx += NT) {
         const int p = idx / KK, o = idx - p * KK;
-        const int q = (o == C::CTR) ? p : (int)qt[idx];
-        float s = 0.f;
-        if (q >= 0) {
-          uint32_t m = mk[idx];
-          while (m) {
-            const int n = __ffs(m) - 1;
-            m &= m - 1;
-            s += gyS[n * P + p];
-          }
-          if (o != C::CTR) {
-            m = mk[q * KK + (KK - 1 - o)];
-            while (m) {
-              const int n = __ffs(m) - 1;
-              m &= m - 1;
-              s += gyS[n * P + q];
-            }
-          }
-        }
-        Wd[idx] = s;
+        float v = 0.f;
+        if (o != C::CTR && qt[idx] >= 0) v = G((o < C::CTR ? o : o - 1) * P + p);
+        Gp[idx] = v;
       }
-      consumer_sync<NT>();  // gyS shares the union with wtab, which the fastest warp writes right after pass A
+      consumer_sync<NT>();
+      // ... plus, on border pixels, the taps folded back by the padding (one thread per entry, fixed order)
+      const int nfd = fptr[Tables<C>::NFP - 1];
+      for (int i = tid; i < nfd; i += NT) {
+        const int dst = fdst[i];
+        float v = Gp[dst];
+        for (int j = fptr[i]; j < fptr[i + 1]; ++j) v += G(fsrc[j]);
+        Gp[dst] = v;
+      }
+      consumer_sync<NT>();
+      if constexpr (!POOLED) {
+        if (tid == 0) mbar_arrive(&gyempty[par]);  // every read of the raw gy happened before the barrier
+      }
+      // S[p][o] = G'[p][o] + G'[q][-o]  (o == ctr: the taps of p that land on p itself, counted once)
+      for (int idx = tid; idx < P * KK; idx += NT) {
+        const int p = idx / KK, o = idx - p * KK;
+        const int q = (o == C::CTR) ? -1 : (int)qt[idx];
+        float v = Gp[idx];
+        if (q >= 0) v += Gp[q * KK + (KK - 1 - o)];
+        Wd[idx] = sgn * v;
+      }
+      // (Wd is next touched after the barriers that follow pass A; Gp is rewritten by the next image after them too)
     }
 
     // ---- pass A: per-pixel |x|^2 and forward-direction dots, streamed over the chunks -----------
@@ -618,28 +697,41 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
       continue;
     } else {
       // ---- backward: stencil coefficients.  Wd currently holds S[p][o] (the gy-only part, computed
-      // before pass A); scale by the inverse norms and close the centre tap, one pixel per thread:
+      // before pass A); scale by the inverse norms and close the centre tap:
       //   Wd[p][o]   = S[p][o] / (N_p N_q)
       //   Wd[p][ctr] = sw - (1/(N_p |x_p|)) * (sum_o Wd[p][o] dot(p, q_o) + sw |x_p|^2),  sw = 2 S[p][ctr] / N_p^2
       const int16_t* qt = reinterpret_cast<const int16_t*>(smem_raw + L.t_q);
       const float* rn = reinterpret_cast<const float*>(smem_raw + L.rn);
       float* Wd = reinterpret_cast<float*>(smem_raw + L.wd);
-      for (int p = tid; p < P; p += NT) {
-        const float ip = inv[p];
+      // eight lanes per pixel share the window offsets; fixed shuffle tree -> deterministic
+      for (int it = tid; it < align_up(P * 8, 32); it += NT) {
+        const int p = it >> 3, g = it & 7;
+        const bool valid = p < P;
+        const float ip = valid ? inv[p] : 0.f;
         float s = 0.f;
+        if (valid) {
 #pragma unroll
-        for (int o = 0; o < KK; ++o) {
-          if (o == C::CTR) continue;
-          const int q = qt[p * KK + o];
-          if (q >= 0) {
-            const float w = Wd[p * KK + o] * (ip * inv[q]);
-            const float d = o > C::CTR ? tfull[p * NV + (o - C::CTR)] : tfull[q * NV + (C::CTR - o)];
-            Wd[p * KK + o] = w;
-            s = fmaf(w, d, s);
+          for (int t = 0; t < (K + 7) / 8; ++t) {
+            const int n = g + 8 * t;          // neighbour number (window order, centre removed)
+            if (n < K) {
+              const int o = n < C::CTR ? n : n + 1;
+              const int q = qt[p * KK + o];
+              if (q >= 0) {
+                const float w = Wd[p * KK + o] * (ip * inv[q]);
+                const float d = o > C::CTR ? tfull[p * NV + (o - C::CTR)] : tfull[q * NV + (C::CTR - o)];
+                Wd[p * KK + o] = w;
+                s = fmaf(w, d, s);
+              }
+            }
           }
         }
-        const float sw = 2.f * Wd[p * KK + C::CTR] * (ip * ip);
-        Wd[p * KK + C::CTR] = sw - rn[p] * (s + sw * tfull[p * NV]);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (valid && g == 0) {
+          const float sw = 2.f * Wd[p * KK + C::CTR] * (ip * ip);
+          Wd[p * KK + C::CTR] = sw - rn[p] * (s + sw * tfull[p * NV]);
+        }
       }
       consumer_sync<NT>();
       NFP_STAMP(2);  // coefficients ready
@@ -671,6 +763,45 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
             }
             if (lane_on) {
               if constexpr (R == 1) {
+#if NFP_PASSB_FFMA2
+                // 3x3: all k*k coefficients of the strip live in registers.  The two channel groups of the pair
+                // share them, so the FMAs run on packed fp32 pairs (lo = group 0, hi = group 1): ptxas folds the
+                // duplicated coefficient into FFMA2's scalar-broadcast operand form (`FFMA2 Rd, Rw.F32, Rx.F32x2,
+                // Rd.F32x2`), i.e. one issue slot per two FMAs and no extra registers for the coefficients.
+                float g0 = 0.f, g1 = 0.f;
+                if constexpr (MODE == MODE_POOL_BWD) {
+                  const float* gp = a.g_gap_x + (size_t)b * a.C + ch * CC + 2 * it * CPW + chslot;
+                  g0 = gp[0] * invP;
+                  g1 = gp[CPW] * invP;
+                }
+                uint64_t out[TW];
+#pragma unroll
+                for (int j = 0; j < TW; ++j) out[j] = pack2(g0, g1);
+#pragma unroll
+                for (int dy = -R; dy <= R; ++dy) {
+                  uint64_t xr[XW];
+#pragma unroll
+                  for (int jj = 0; jj < XW; ++jj)
+                    xr[jj] = pack2(ldx<T>(pa + NFP_OFF(dy, jj)), ldx<T>(pa + GSTRIDE + NFP_OFF(dy, jj)));
+                  // dx outer, j inner: consecutive FMAs go to different accumulators (no 4-cycle chains)
+#pragma unroll
+                  for (int dx = -R; dx <= R; ++dx)
+#pragma unroll
+                    for (int j = 0; j < TW; ++j) {
+                      if (j + dx + XOFF >= 0 && j + dx + XOFF < XW) {
+                        const float w = wr[j][(dy + R) * k + dx + R];
+                        out[j] = fma2(pack2(w, w), xr[j + dx + XOFF], out[j]);
+                      }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < TW; ++j) {
+                  float lo, hi;
+                  unpack2(out[j], lo, hi);
+                  stx<T>(sb + toff + j * ESZ, lo);
+                  stx<T>(sb + GSTRIDE + toff + j * ESZ, hi);
+                }
+#else
                 // 3x3: all k*k coefficients of the strip live in registers
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -698,7 +829,50 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
 #pragma unroll
                   for (int j = 0; j < TW; ++j) stx<T>(sb + h * GSTRIDE + toff + j * ESZ, out[j]);
                 }
+#endif
               } else {
+#if NFP_PASSB_FFMA2
+                // wider windows: the coefficients of ONE window row at a time (register budget), each row
+                // loaded once and applied to both channel groups of the pair as packed fp32 pairs (FFMA2 with
+                // the coefficient as scalar-broadcast operand, see the 3x3 branch)
+                float g0 = 0.f, g1 = 0.f;
+                if constexpr (MODE == MODE_POOL_BWD) {
+                  const float* gp = a.g_gap_x + (size_t)b * a.C + ch * CC + 2 * it * CPW + chslot;
+                  g0 = gp[0] * invP;
+                  g1 = gp[CPW] * invP;
+                }
+                uint64_t out[TW];
+#pragma unroll
+                for (int j = 0; j < TW; ++j) out[j] = pack2(g0, g1);
+#pragma unroll
+                for (int dy = -R; dy <= R; ++dy) {
+                  float wrow[TW][k];
+#pragma unroll
+                  for (int j = 0; j < TW; ++j)
+#pragma unroll
+                    for (int dx = 0; dx < k; ++dx) wrow[j][dx] = wdp[j * KK + (dy + R) * k + dx];
+                  uint64_t xr[XW];
+#pragma unroll
+                  for (int jj = 0; jj < XW; ++jj)
+                    xr[jj] = pack2(ldx<T>(pa + NFP_OFF(dy, jj)), ldx<T>(pa + GSTRIDE + NFP_OFF(dy, jj)));
+#pragma unroll
+                  for (int dx = -R; dx <= R; ++dx)
+#pragma unroll
+                    for (int j = 0; j < TW; ++j) {
+                      if (j + dx + XOFF >= 0 && j + dx + XOFF < XW) {
+                        const float w = wrow[j][dx + R];
+                        out[j] = fma2(pack2(w, w), xr[j + dx + XOFF], out[j]);
+                      }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < TW; ++j) {
+                  float lo, hi;
+                  unpack2(out[j], lo, hi);
+                  stx<T>(sb + toff + j * ESZ, lo);
+                  stx<T>(sb + GSTRIDE + toff + j * ESZ, hi);
+                }
+#else
                 // wider windows: the coefficients of ONE window row at a time (register budget), each row
                 // loaded once and applied to both channel groups of the pair
                 float out[2][TW];
@@ -735,6 +909,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
                   for (int j = 0; j < TW; ++j) stx<T>(sb + h * GSTRIDE + toff + j * ESZ, out[h][j]);
+#endif
               }
             }
             fence_async_smem();
@@ -751,6 +926,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, C::MINB) stream_kernel(const St
           if (++slot == nst) { slot = 0; ph ^= 1; }
         }
         NFP_STAMP(3);  // pass B done (this warp)
+        if constexpr (R != 1) {
+        }
         if (lane == 0) bulk_wait_read<0>();  // staging is part of the union the next image overwrites
       }
       consumer_sync<NT>();
@@ -850,7 +1027,7 @@ int launch_mode(const KParams& P, StreamArgs a, cudaStream_t stream) {
   static const int use_pdl = env_int("NFPB200_PDL", 1);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((kNW + 1) * 32);
+  cfg.blockDim = dim3(block_threads(MODE, kNW));
   cfg.dynamicSmemBytes = pl.smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -863,7 +1040,7 @@ int launch_mode(const KParams& P, StreamArgs a, cudaStream_t stream) {
     cudaFuncAttributes fa{};
     cudaFuncGetAttributes(&fa, kern);
     fprintf(stderr, "[nfpb200] launch failed (%d): grid %d block %d dyn smem %zu static %zu regs %d maxThreads %d\n",
-            (int)lrc, grid, (kNW + 1) * 32, pl.smem, fa.sharedSizeBytes, fa.numRegs, fa.maxThreadsPerBlock);
+            (int)lrc, grid, block_threads(MODE, kNW), pl.smem, fa.sharedSizeBytes, fa.numRegs, fa.maxThreadsPerBlock);
   }
   return (int)lrc;
 }
