@@ -47,7 +47,7 @@ int make_params(const nfpb200_desc_t* d, KParams* out) {
   return NFPB200_OK;
 }
 
-// 2 = fused/stream, 1 = fused/slab, 0 = generic, <0 = error
+// 3 = planar, 2 = fused/stream, 1 = fused/slab, 0 = generic, <0 = error
 int choose_path(const nfpb200_desc_t* d, const KParams& P, int op) {
   // NFPB200_FUSED_IMPL=slab selects the first-generation slab kernels (A/B comparisons)
   static const bool prefer_slab = [] {
@@ -59,7 +59,14 @@ int choose_path(const nfpb200_desc_t* d, const KParams& P, int op) {
   const int fused = can_stream ? 2 : (can_slab ? 1 : 0);
   if (d->path == NFPB200_PATH_FUSED) return fused ? fused : NFPB200_EUNSUPPORTED;
   if (d->path == NFPB200_PATH_GENERIC) return 0;
-  return fused;
+  if (fused) return fused;
+  // large or odd-sized maps (the multi-stage heads' 112x112 ... 28x28 maps): per-pixel planar kernels
+  return planar_supported(P, d->dtype, d->measure, op) ? 3 : 0;
+}
+
+size_t path_workspace_bytes(int path, const nfpb200_desc_t* d, const KParams& P, int op) {
+  if (path == 3) return planar_workspace_bytes(P, op);
+  return path ? 0 : generic_workspace_bytes(P, d->dtype, d->measure, op);
 }
 
 int check_device() {
@@ -118,7 +125,7 @@ int nfpb200_workspace_bytes(const nfpb200_desc_t* desc, int32_t op, size_t* byte
   if (!bytes || op < NFPB200_OP_FORWARD || op > NFPB200_OP_POOL_BACKWARD) return NFPB200_EINVAL;
   int path = choose_path(desc, P, op);
   if (path < 0) return path;
-  *bytes = path ? 0 : generic_workspace_bytes(P, desc->dtype, desc->measure, op);
+  *bytes = path_workspace_bytes(path, desc, P, op);
   return NFPB200_OK;
 }
 
@@ -130,8 +137,9 @@ int nfpb200_describe_path(const nfpb200_desc_t* desc, int32_t op, char* buf, siz
   int path = choose_path(desc, P, op);
   if (path < 0) return path;
   snprintf(buf, buf_bytes, "%s",
-           path == 2 ? stream_name(P, desc->dtype, desc->measure, op)
-                     : (path == 1 ? fused_name(P, desc->dtype, desc->measure, op) : "generic/pairs"));
+           path == 3 ? planar_name(P, desc->dtype, op)
+                     : (path == 2 ? stream_name(P, desc->dtype, desc->measure, op)
+                                  : (path == 1 ? fused_name(P, desc->dtype, desc->measure, op) : "generic/pairs")));
   return NFPB200_OK;
 }
 
@@ -142,7 +150,7 @@ int nfpb200_launch_count(const nfpb200_desc_t* desc, int32_t op, int32_t* launch
   if (!launches || op < NFPB200_OP_FORWARD || op > NFPB200_OP_POOL_BACKWARD) return NFPB200_EINVAL;
   int path = choose_path(desc, P, op);
   if (path < 0) return path;
-  *launches = path ? 1 : generic_launch_count(P, desc->dtype, desc->measure, op);
+  *launches = path == 3 ? planar_launch_count(op) : (path ? 1 : generic_launch_count(P, desc->dtype, desc->measure, op));
   return NFPB200_OK;
 }
 
@@ -156,7 +164,7 @@ static inline bool misaligned(const void* p) { return (reinterpret_cast<uintptr_
   if (rc) return rc;                                                                          \
   const int path = choose_path(desc, P, OP);                                                  \
   if (path < 0) return path;                                                                  \
-  const size_t need = path ? 0 : generic_workspace_bytes(P, desc->dtype, desc->measure, OP);  \
+  const size_t need = path_workspace_bytes(path, desc, P, OP);                                \
   if (need > 0 && (!workspace || workspace_bytes < need)) return NFPB200_EWORKSPACE;          \
   LaunchCtx ctx{(cudaStream_t)stream, workspace, workspace_bytes};
 
@@ -165,6 +173,7 @@ int nfpb200_forward(const nfpb200_desc_t* desc, const void* x, void* y, void* wo
   if (!x || !y) return NFPB200_EINVAL;
   if (misaligned(x) || misaligned(y)) return NFPB200_EALIGN;
   NFP_PROLOGUE(NFPB200_OP_FORWARD)
+  if (path == 3) return planar_forward(P, desc->dtype, x, y, ctx);
   if (path == 2) return stream_forward(P, desc->dtype, x, y, ctx);
   return path ? fused_forward(P, desc->dtype, x, y, ctx) : generic_forward(P, desc->dtype, desc->measure, x, y, ctx);
 }
@@ -174,6 +183,7 @@ int nfpb200_backward(const nfpb200_desc_t* desc, const void* x, const void* gy, 
   if (!x || !gy || !gx) return NFPB200_EINVAL;
   if (misaligned(x) || misaligned(gy) || misaligned(gx)) return NFPB200_EALIGN;
   NFP_PROLOGUE(NFPB200_OP_BACKWARD)
+  if (path == 3) return planar_backward(P, desc->dtype, x, gy, gx, ctx);
   if (path == 2) return stream_backward(P, desc->dtype, x, gy, gx, ctx);
   return path ? fused_backward(P, desc->dtype, x, gy, gx, ctx)
               : generic_backward(P, desc->dtype, desc->measure, x, gy, gx, ctx);

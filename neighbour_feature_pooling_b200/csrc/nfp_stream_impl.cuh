@@ -35,6 +35,7 @@
 #include <type_traits>
 
 #include "nfp_common.cuh"
+#include "nfp_ptx.cuh"
 #include "nfp_stream.h"
 
 // pass B on packed fp32 pairs (FFMA2 with scalar-broadcast coefficients) vs scalar FFMA: A/B switch
@@ -186,99 +187,8 @@ const Tables<C>* tables_for(int pad_mode) {
   return e == cudaSuccess ? p : nullptr;
 }
 
-// ---- PTX helpers: mbarrier, TMA bulk copies, named barriers, packed fp32 ---------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-template <int NTHREADS>
-__device__ __forceinline__ void consumer_sync() {  // named barrier 1: the consumer warps only
-  asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
-}
-
-// programmatic dependent launch (PDL): wait for the preceding grid / let the next grid start launching
-__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
+using namespace ptx;
 #define NFP_STAMP(k) do { if (a.dbg && tid == 0 && img == 0) a.dbg[(size_t)blockIdx.x * 8 + (k)] = globaltimer_ns(); } while (0)
-
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ float sum2(uint64_t v) {
-  float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-  return lo + hi;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {  // FFMA2 on sm_100
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-
-// element load from shared memory at a byte address
-template <typename T> __device__ __forceinline__ float ldx(const unsigned char* p);
-template <> __device__ __forceinline__ float ldx<float>(const unsigned char* p) {
-  return *reinterpret_cast<const float*>(p);
-}
-template <> __device__ __forceinline__ float ldx<__nv_bfloat16>(const unsigned char* p) {
-  return __uint_as_float(((uint32_t) * reinterpret_cast<const unsigned short*>(p)) << 16);
-}
-template <typename T> __device__ __forceinline__ void stx(unsigned char* p, float v);
-template <> __device__ __forceinline__ void stx<float>(unsigned char* p, float v) { *reinterpret_cast<float*>(p) = v; }
-template <> __device__ __forceinline__ void stx<__nv_bfloat16>(unsigned char* p, float v) {
-  *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16_rn(v);
-}
 
 constexpr int kMaxStages = 8;
 // warps of a CTA: NW consumers and one producer (TMA issue)

@@ -98,6 +98,50 @@ FUSED_SHAPES = [(5, 64, 7, 7, 1), (3, 512, 7, 7, 1), (2, 960, 7, 7, 1), (3, 256,
                 (3, 128, 7, 7, 2), (2, 512, 7, 7, 2), (2, 64, 14, 14, 2), (2, 256, 14, 14, 2)]
 
 
+PLANAR_SHAPES = [(2, 16, 112, 112, 1), (2, 24, 56, 56, 1), (3, 40, 28, 28, 1), (2, 7, 9, 13, 1), (2, 5, 3, 3, 1),
+                 (2, 12, 28, 28, 2), (1, 6, 11, 13, 3), (3, 33, 7, 7, 1), (2, 10, 5, 9, 2),
+                 (2, 5, 8, 6, 1), (70, 3, 12, 8, 1), (1, 4, 16, 20, 2)]   # row granule 2 / many images
+PLANAR_BAND = {(16, 112, 112), (24, 56, 56), (40, 28, 28), (12, 28, 28), (5, 8, 6), (3, 12, 8), (4, 16, 20)}
+
+
+@pytest.mark.parametrize("shape", PLANAR_SHAPES, ids=lambda s: "x".join(map(str, s[:4])) + f"_r{s[4]}")
+@pytest.mark.parametrize("mode", ["reflect", "zeros", "replicate"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("similarity", [True, False], ids=["sim", "dist"])
+def test_planar_cosine_vs_oracle(shape, mode, dtype, similarity, cuda_device):
+    """Maps the streaming kernels do not cover (multi-stage heads, texture_pooling.py:211-268: 16x112x112 ...;
+    odd sizes / channel counts) take the planar kernels: same closed forms, no atomics."""
+    B, C, H, W, R = shape
+    if mode == "reflect" and R >= min(H, W):
+        pytest.skip("reflect padding needs pad < dim")
+    K = (2 * R + 1) ** 2 - 1
+    gen = torch.Generator().manual_seed(B * 1000 + C + H + R)
+    x = torch.randn(B, C, H, W, generator=gen)
+    if C % 3 == 0:
+        x = x.relu()
+    x[0, :, 0, 0] = 0.0
+    x[-1, :, H - 1, W - 1] *= 1e-9
+    g = torch.randn(B, K, H, W, generator=gen)
+    if dtype == torch.bfloat16:
+        x, g = x.bfloat16().float(), g.bfloat16().float()
+    kw = dict(R=R, measure="cosine", padding=R, padding_mode=mode, similarity=similarity)
+    cfg = NFPPooling(C, **kw).config
+    # TMA-staged row bands where planes and row groups are 16-byte aligned, plain coalesced loads otherwise
+    want = "planar/band" if (C, H, W) in PLANAR_BAND else "planar/table"
+    if R > 2:
+        want = "generic/pairs"   # 7x7 windows and wider: generic kernels
+    assert NF.describe(shape[:4], dtype, cfg) == want
+    assert NF.describe(shape[:4], dtype, cfg, op=1) == want
+    y_ref, gx_ref = O.nfp_forward_backward(x.double(), g.double(), **kw)
+    y, gx = _run(x, g, kw, cuda_device, dtype=dtype)
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert rel_err(y, y_ref) < tol
+    assert rel_err(gx, gx_ref) < tol
+    if R <= 2:  # bit-reproducible (gather form, no atomics)
+        y2, gx2 = _run(x, g, kw, cuda_device, dtype=dtype)
+        assert torch.equal(y, y2) and torch.equal(gx, gx2)
+
+
 @pytest.mark.parametrize("shape", FUSED_SHAPES, ids=lambda s: "x".join(map(str, s[:4])) + f"_r{s[4]}")
 @pytest.mark.parametrize("mode", ["reflect", "zeros", "replicate"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
