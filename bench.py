@@ -205,6 +205,39 @@ class LayerBench:
         self.fwd(i)
         self.bwd(i)
 
+    # pooled mode (the nfp_pooling head, models/NFP_Pooling.py:25-36): GAP(x) and GAP(NFP(x)) from one pass over x,
+    # backward from their two gradients; the similarity map is never written
+    def pool_setup(self):
+        mkf = lambda *s: torch.randn(*s, device=self.dev, dtype=torch.float32)
+        self.gap_x = [torch.empty(self.B, self.C, device=self.dev) for _ in range(self.nbuf)]
+        self.gap_n = [torch.empty(self.B, self.K, device=self.dev) for _ in range(self.nbuf)]
+        self.g_gap_x = [mkf(self.B, self.C) for _ in range(self.nbuf)]
+        self.g_gap_n = [mkf(self.B, self.K) for _ in range(self.nbuf)]
+        c = self.capi
+        self.path_pool = c.describe_path(self.desc, c.OP_POOL_FORWARD), c.describe_path(self.desc, c.OP_POOL_BACKWARD)
+        wsn = max(c.workspace_bytes(self.desc, c.OP_POOL_FORWARD), c.workspace_bytes(self.desc, c.OP_POOL_BACKWARD))
+        if wsn > self.ws_n:
+            self.ws = torch.empty(wsn, dtype=torch.uint8, device=self.dev)
+            self.ws_n = wsn
+
+    def pool_fwd(self, i):
+        s = torch.cuda.current_stream(self.dev).cuda_stream
+        rc = self.lib.nfpb200_pool_forward(ctypes.byref(self.desc), self.x[i].data_ptr(), self.gap_x[i].data_ptr(),
+                                           self.gap_n[i].data_ptr(), self.ws.data_ptr() if self.ws_n else None,
+                                           self.ws_n, s)
+        self.capi.check(rc, "nfpb200_pool_forward")
+
+    def pool_bwd(self, i):
+        s = torch.cuda.current_stream(self.dev).cuda_stream
+        rc = self.lib.nfpb200_pool_backward(ctypes.byref(self.desc), self.x[i].data_ptr(), self.g_gap_x[i].data_ptr(),
+                                            self.g_gap_n[i].data_ptr(), self.gx[i].data_ptr(),
+                                            self.ws.data_ptr() if self.ws_n else None, self.ws_n, s)
+        self.capi.check(rc, "nfpb200_pool_backward")
+
+    def pool_step(self, i):
+        self.pool_fwd(i)
+        self.pool_bwd(i)
+
     def _graph(self, fn, n, start):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -246,25 +279,59 @@ class LayerBench:
 
 
 def e2e_through_module(dev, B, C, H, W, R, dtype_name, steps, warmup, sampler, barrier):
-    """Public-API path with host buffers: H2D(x, gy) -> NFPPooling fwd -> autograd bwd -> D2H(y, gx)."""
+    """Public-API path with host buffers: H2D(x, gy) -> NFPPooling fwd -> autograd bwd -> D2H(y, gx), every step.
+
+    The three legs run on three CUDA streams over three device buffer sets, so the host->device copy of step i+1,
+    the kernels of step i and the device->host copy of step i-1 overlap (PCIe is full duplex); every step still
+    moves all of its inputs and results through pinned host memory inside the timed region."""
     import neighbour_feature_pooling_b200 as nfpb
     tdtype = torch.float32 if dtype_name == "fp32" else torch.bfloat16
     K = (2 * R + 1) ** 2 - 1
     layer = nfpb.NFPPooling(C, R=R, measure="cosine", padding=R).to(dev)
     gen = torch.Generator().manual_seed(1)
-    nh = 2  # two host buffer sets, alternated
+    nh, nd = 2, 3  # host buffer sets (alternated), device buffer sets (pipeline depth)
     hx = [torch.randn(B, C, H, W, generator=gen).to(tdtype).pin_memory() for _ in range(nh)]
     hg = [torch.randn(B, K, H, W, generator=gen).to(tdtype).pin_memory() for _ in range(nh)]
     hy = [torch.empty(B, K, H, W, dtype=tdtype).pin_memory() for _ in range(nh)]
     hgx = [torch.empty(B, C, H, W, dtype=tdtype).pin_memory() for _ in range(nh)]
+    dx = [torch.empty(B, C, H, W, dtype=tdtype, device=dev) for _ in range(nd)]
+    dg = [torch.empty(B, K, H, W, dtype=tdtype, device=dev) for _ in range(nd)]
+    s_in, s_cmp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+    ev_in = [torch.cuda.Event() for _ in range(nd)]
+    ev_cmp = [None] * nd   # kernels of the step that last used device set j
+    ev_out = [None] * nd   # D2H of the step that last used device set j
+    keep = [None] * nd     # that step's y / grad_x: alive until its D2H is ordered before any reuse of their memory
 
     def one(i):
-        x = hx[i % nh].to(dev, non_blocking=True).requires_grad_(True)
-        g = hg[i % nh].to(dev, non_blocking=True)
-        y = layer(x)
-        y.backward(g)
-        hy[i % nh].copy_(y.detach(), non_blocking=True)
-        hgx[i % nh].copy_(x.grad, non_blocking=True)
+        j, h = i % nd, i % nh
+        with torch.cuda.stream(s_in):
+            if ev_cmp[j] is not None:
+                s_in.wait_event(ev_cmp[j])          # the kernels that read this device set are done
+            dx[j].copy_(hx[h], non_blocking=True)
+            dg[j].copy_(hg[h], non_blocking=True)
+            ev_in[j].record(s_in)
+        with torch.cuda.stream(s_cmp):
+            s_cmp.wait_event(ev_in[j])
+            if ev_out[j] is not None:
+                s_cmp.wait_event(ev_out[j])         # outputs of step i - nd have left the device:
+            keep[j] = None                          # their blocks may be reused by this stream from here on
+            x = dx[j].detach().requires_grad_(True)
+            y = layer(x)
+            y.backward(dg[j])
+            keep[j] = (y.detach(), x.grad)
+            ev_cmp[j] = torch.cuda.Event()
+            ev_cmp[j].record(s_cmp)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_cmp[j])
+            hy[h].copy_(keep[j][0], non_blocking=True)
+            hgx[h].copy_(keep[j][1], non_blocking=True)
+            ev_out[j] = torch.cuda.Event()
+            ev_out[j].record(s_out)
+
+    def drain():
+        cur = torch.cuda.current_stream(dev)
+        for st in (s_in, s_cmp, s_out):
+            cur.wait_stream(st)
 
     for i in range(max(3, warmup)):
         one(i)
@@ -274,8 +341,11 @@ def e2e_through_module(dev, B, C, H, W, R, dtype_name, steps, warmup, sampler, b
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.tag = "e2e"
     e0.record()
+    for st in (s_in, s_cmp, s_out):
+        st.wait_event(e0)
     for i in range(steps):
         one(i)
+    drain()
     e1.record()
     e1.synchronize()
     sampler.tag = None
@@ -455,6 +525,20 @@ def main():
     t_e2e = max_over_ranks(t_e2e)
     e2e_value = world * e2e_steps * B / t_e2e
 
+    # ---- pooled mode: the nfp_pooling head path, same shape, device resident -----------------
+    lb.pool_setup()
+    n_pool = min(args.steps, 300)
+    t_pool = lb.timed(lb.pool_step, n_pool, 5, sampler, "pooled") / n_pool
+    t_pool_f = lb.timed(lb.pool_fwd, n_pool, 5, sampler, "pooled") / n_pool
+    t_pool_b = lb.timed(lb.pool_bwd, n_pool, 5, sampler, "pooled") / n_pool
+    pool_fb = B * (C * H * W * lb.esz + (C + lb.K) * 4)                # read x; write GAP(x), GAP(NFP(x))
+    pool_bb = B * (2 * C * H * W * lb.esz + (C + lb.K) * 4)            # read x and the two gradients; write grad_x
+    pooled = {"workload": "nfp_pooling head (GAP(x), GAP(NFP(x)) fwd + bwd) " + workload_name(B, C, H, W, R, args.dtype)[20:],
+              "maps_per_s": B / t_pool, "us_per_step": t_pool * 1e6, "us_fwd": t_pool_f * 1e6, "us_bwd": t_pool_b * 1e6,
+              "bytes_per_step": pool_fb + pool_bb, "step_frac": (pool_fb + pool_bb) / t_pool / 1e9 / hbm_peak,
+              "fwd_frac": pool_fb / t_pool_f / 1e9 / hbm_peak, "bwd_frac": pool_bb / t_pool_b / 1e9 / hbm_peak,
+              "path": {"forward": lb.path_pool[0], "backward": lb.path_pool[1]}}
+
     # ---- the other configs[1] cases (reported, not part of `value`) -------------------------------------
     sweep = []
     if not args.no_sweep and rank == 0:
@@ -513,7 +597,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": t_e2e / e2e_steps * 1e3,
                     "api": "NFPPooling(C,R,'cosine',padding=R).forward + autograd backward; pinned host x, grad_y -> "
-                           "device; y, grad_x -> pinned host"},
+                           "device; y, grad_x -> pinned host, every step; copy-in / kernels / copy-out on three "
+                           "streams over three device buffer sets (pipelined, PCIe full duplex)"},
             "gpu_launches": args.steps * lb.launches,
             "roofline": {"bound": "hbm", "kernel": "nfpb200_backward (" + lb.path_bwd + ")", "achieved": achieved,
                          "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
@@ -529,6 +614,7 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        line["pooled"] = pooled
         if sweep:
             line["sweep"] = sweep
         if train is not None:

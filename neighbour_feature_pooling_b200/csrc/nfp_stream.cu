@@ -66,6 +66,7 @@ int stream_pool_backward(const KParams& P, int dtype, const void* x, const float
                          void* gx, const LaunchCtx& ctx) {
   stream::StreamArgs a{};
   a.x = x; a.g_gap_x = g_gap_x; a.g_gap_nfp = g_gap_nfp; a.gx = gx;
+  a.ggx_tma = (P.C % 4 == 0) && (reinterpret_cast<uintptr_t>(g_gap_x) % 16 == 0);
   return run(P, dtype, stream::MODE_POOL_BWD, a, ctx.stream);
 }
 

@@ -207,12 +207,12 @@ template <typename T, class C, int MODE, int NW>
 struct Smem {
   static constexpr bool BWD = (MODE == MODE_BWD || MODE == MODE_POOL_BWD);
   static constexpr int ESZ = (int)sizeof(T);
-  int slot_stride, lead, ring, bars, tfull, inv, tabs, gyraw, uni, total;
+  int slot_stride, lead, ring, ggx, bars, tfull, inv, tabs, gyraw, uni, total;
   int t_fv, t_fd, t_q, t_fsrc, t_fdst, t_fptr;  // copies of the stencil tables
   int rn, wd, gp;                              // backward: 1/(N |x|) per pixel, stencil coefficients, stencil-warp scratch
   int wtab, stg, ytab;                         // inside the union
   int stg_warp;                                // staging bytes per warp (two buffers)
-  __host__ __device__ Smem(int CC, int nst) {
+  __host__ __device__ Smem(int CC, int nst, int Cfull) {
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 127) & ~127; return r; };
     // everything whose size is known at compile time comes first (so its address is a constant in the
@@ -253,6 +253,7 @@ struct Smem {
     slot_stride = align_up(CC * C::P * ESZ + C::HALO * ESZ, 128);
     lead = take(kLeadPad);
     ring = take(nst * slot_stride);
+    ggx = take(MODE == MODE_POOL_BWD ? 2 * Cfull * 4 : 0);  // pooled backward: d out / d GAP(x) of two images in flight
     total = o;
   }
 };
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int nst = a.nst, NCH = a.NCH, CC = a.CC;
-  const Smem<T, C, MODE, NW> L(CC, nst);
+  const Smem<T, C, MODE, NW> L(CC, nst, a.C);
   unsigned char* ring = smem_raw + L.ring;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
   uint64_t* empty = full + kMaxStages;
@@ -326,6 +327,13 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
           mbar_expect_tx(&gyfull[par], (uint32_t)GY_BYTES);
           bulk_g2s(smem_raw + L.gyraw + par * GY_STRIDE, reinterpret_cast<const T*>(a.gy) + (size_t)b * K * P,
                    (uint32_t)GY_BYTES, &gyfull[par]);
+        }
+
+        if (MODE == MODE_POOL_BWD && a.ggx_tma) {  // the image's d out / d GAP(x): C floats, one bulk copy
+          const int par = img & 1;
+          mbar_wait(&gyempty[par], ((img >> 1) & 1) ^ 1);
+          mbar_expect_tx(&gyfull[par], (uint32_t)a.C * 4u);
+          bulk_g2s(smem_raw + L.ggx + par * a.C * 4, a.g_gap_x + (size_t)b * a.C, (uint32_t)a.C * 4u, &gyfull[par]);
         }
         const unsigned char* xb = reinterpret_cast<const unsigned char*>(a.x) + (size_t)b * a.C * P * ESZ;
         for (int pass = 0; pass < npass; ++pass) {
@@ -391,6 +399,12 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
       if constexpr (POOLED) {
         // d GAP(y) / dy: the same value on every pixel of a tap plane
         if (tid < K) reinterpret_cast<float*>(smem_raw + L.gyraw)[tid] = a.g_gap_nfp[(size_t)b * K + tid] * (1.f / (float)P);
+        if constexpr (MODE == MODE_POOL_BWD) {
+          if (!a.ggx_tma) {  // rows not 16-byte aligned / sized: no bulk copy, stage them with plain loads
+            float* gs = reinterpret_cast<float*>(smem_raw + L.ggx) + (img & 1) * a.C;
+            for (int i = tid; i < a.C; i += NT) gs[i] = a.g_gap_x[(size_t)b * a.C + i];
+          }
+        }
         consumer_sync<NT>();
       } else {
         mbar_wait(&gyfull[par], (img >> 1) & 1);
@@ -443,8 +457,10 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
           mbar_wait(&full[slot], ph);
           const unsigned char* sl = ring + slot * L.slot_stride;
           if constexpr (MODE == MODE_POOL_FWD) {
-            // GAP(x) of this chunk's channels (NFP_Pooling.py:27): one lane per channel plane; the
-            // job rotates over the warps chunk by chunk
+            // GAP(x) of this chunk's channels (NFP_Pooling.py:27): one lane per channel plane; the job rotates
+            // over the warps chunk by chunk.  (Measured alternative, not kept: row sums from the strips pass A
+            // already holds in registers + a shuffle tree over the strips -- 11.4 vs 8.7 us, shuffles share the
+            // shared-memory data path and the extra live values spill.)
             const int w0 = (ch * 2) % NW;
             for (int c = ((warp - w0 + NW) % NW) * 32 + lane; c < CC; c += NT) {
               const unsigned char* pl = sl + c * P * ESZ;
@@ -500,6 +516,10 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
           mbar_wait(&full[slot], ph);
           const unsigned char* sl = ring + slot * L.slot_stride;
           if constexpr (MODE == MODE_POOL_FWD) {
+            // GAP(x) of this chunk's channels (NFP_Pooling.py:27): one lane per channel plane; the job rotates
+            // over the warps chunk by chunk.  (Measured alternative, not kept: row sums from the strips pass A
+            // already holds in registers + a shuffle tree over the strips -- 11.4 vs 8.7 us, shuffles share the
+            // shared-memory data path and the extra live values spill.)
             const int w0 = (ch * 2) % NW;
             for (int c = ((warp - w0 + NW) % NW) * 32 + lane; c < CC; c += NT) {
               const unsigned char* pl = sl + c * P * ESZ;
@@ -652,6 +672,11 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
         const float invP = 1.f / (float)P;
         unsigned char* gxb = reinterpret_cast<unsigned char*>(a.gx) + (size_t)b * a.C * P * ESZ;
         if (resident) { slot = slot0; ph = ph0; }  // re-walk the slots pass A left in place
+        const float* ggx = nullptr;
+        if constexpr (MODE == MODE_POOL_BWD) {
+          if (a.ggx_tma) mbar_wait(&gyfull[img & 1], (img >> 1) & 1);  // bulk copy issued by the producer
+          ggx = reinterpret_cast<const float*>(smem_raw + L.ggx) + (img & 1) * a.C;
+        }
         int nstore = 0;
         const float* wdp = Wd + (pos * TW) * KK;
         float wr[(R == 1) ? TW : 1][(R == 1) ? KK : 1];
@@ -680,7 +705,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
                 // Rd.F32x2`), i.e. one issue slot per two FMAs and no extra registers for the coefficients.
                 float g0 = 0.f, g1 = 0.f;
                 if constexpr (MODE == MODE_POOL_BWD) {
-                  const float* gp = a.g_gap_x + (size_t)b * a.C + ch * CC + 2 * it * CPW + chslot;
+                  const float* gp = ggx + ch * CC + 2 * it * CPW + chslot;
                   g0 = gp[0] * invP;
                   g1 = gp[CPW] * invP;
                 }
@@ -719,7 +744,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
                   float out[TW];
                   float g0 = 0.f;
                   if constexpr (MODE == MODE_POOL_BWD)
-                    g0 = a.g_gap_x[(size_t)b * a.C + ch * CC + (2 * it + h) * CPW + chslot] * invP;
+                    g0 = ggx[ch * CC + (2 * it + h) * CPW + chslot] * invP;
 #pragma unroll
                   for (int j = 0; j < TW; ++j) out[j] = g0;
 #pragma unroll
@@ -747,7 +772,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
                 // the coefficient as scalar-broadcast operand, see the 3x3 branch)
                 float g0 = 0.f, g1 = 0.f;
                 if constexpr (MODE == MODE_POOL_BWD) {
-                  const float* gp = a.g_gap_x + (size_t)b * a.C + ch * CC + 2 * it * CPW + chslot;
+                  const float* gp = ggx + ch * CC + 2 * it * CPW + chslot;
                   g0 = gp[0] * invP;
                   g1 = gp[CPW] * invP;
                 }
@@ -790,7 +815,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
                 for (int h = 0; h < 2; ++h) {
                   float g0 = 0.f;
                   if constexpr (MODE == MODE_POOL_BWD)
-                    g0 = a.g_gap_x[(size_t)b * a.C + ch * CC + (2 * it + h) * CPW + chslot] * invP;
+                    g0 = ggx[ch * CC + (2 * it + h) * CPW + chslot] * invP;
 #pragma unroll
                   for (int j = 0; j < TW; ++j) out[h][j] = g0;
                 }
@@ -836,11 +861,13 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
           if (++slot == nst) { slot = 0; ph ^= 1; }
         }
         NFP_STAMP(3);  // pass B done (this warp)
-        if constexpr (R != 1) {
-        }
         if (lane == 0) bulk_wait_read<0>();  // staging is part of the union the next image overwrites
       }
       consumer_sync<NT>();
+      if constexpr (MODE == MODE_POOL_BWD) {
+        // every warp is past its last read of this image's g_gap_x
+        if (tid == 0 && a.ggx_tma) mbar_arrive(&gyempty[img & 1]);
+      }
     }
   }
   if (BWD && lane == 0) bulk_wait_all();
@@ -890,7 +917,7 @@ Plan plan_for(const KParams& P) {
     const int budget = kSmemPerSM / ctas - 2048;  // the runtime reserves 1 KB per CTA; 1 KB slack
     static const int max_stages = env_int("NFPB200_MAX_STAGES", kMaxStages);
     for (int nst = max_stages < kMaxStages ? max_stages : kMaxStages; nst >= 2; --nst) {  // as many stages as fit
-      Smem<T, C, MODE, kNW> L(pl.CC, nst);
+      Smem<T, C, MODE, kNW> L(pl.CC, nst, P.C);
       if (L.total > budget) continue;
       pl.nst = nst;
       pl.smem = (size_t)L.total;

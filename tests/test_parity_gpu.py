@@ -265,6 +265,41 @@ def test_pooled_head_equals_map_then_gap(shape, cuda_device):
     assert rel_err(xa.grad.cpu(), xb.grad.cpu()) < FP32_TOL
 
 
+@pytest.mark.parametrize("shape", [(5, 64, 7, 7), (300, 16, 7, 7), (3, 6, 14, 14)], ids=lambda s: "x".join(map(str, s)))
+def test_pool_backward_gradient_row_alignment(shape, cuda_device):
+    """nfpb200_pool_backward stages d out / d GAP(x) with one TMA bulk copy per image when its rows are 16-byte
+    aligned and sized, with plain loads otherwise (C % 4 != 0, or a gradient view at an odd offset): same bits."""
+    import ctypes
+    from neighbour_feature_pooling_b200 import _capi
+    B, C, H, W = shape
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(B, C, H, W, generator=gen).to(cuda_device)
+    ggn = torch.randn(B, 8, generator=gen).to(cuda_device)
+    vals = torch.randn(B, C, generator=gen).to(cuda_device)
+    buf = torch.empty(B * C + 4, device=cuda_device)
+    desc = _capi.make_desc(_capi.F32, B, C, H, W, 1, 1, 1, 1, "reflect", "cosine", True, False, 1e-6, 1, 1e-6, "auto")
+    assert _capi.describe_path(desc, _capi.OP_POOL_BACKWARD).startswith("fused/stream")
+    lib = _capi.load()
+    outs = []
+    for off in (0, 1):   # 0: aligned rows, 1: the same values 4 bytes further (misaligned)
+        ggx = buf[off:off + B * C].view(B, C)
+        ggx.copy_(vals)
+        assert (ggx.data_ptr() % 16 == 0) == (off == 0)
+        gx = torch.empty_like(x)
+        rc = lib.nfpb200_pool_backward(ctypes.byref(desc), x.data_ptr(), ggx.data_ptr(), ggn.data_ptr(), gx.data_ptr(),
+                                       None, 0, torch.cuda.current_stream().cuda_stream)
+        _capi.check(rc, "nfpb200_pool_backward")
+        torch.cuda.synchronize()
+        outs.append(gx.cpu())
+    assert torch.equal(outs[0], outs[1])
+    # and against autograd through the map-mode kernels
+    cfg = NFPPooling(C, R=1, measure="cosine", padding=1).config
+    xb = x.clone().requires_grad_(True)
+    yb = NF.nfp_similarity(xb, cfg)
+    ((xb.mean((2, 3)) * vals).sum() + (yb.mean((2, 3)) * ggn).sum()).backward()
+    assert rel_err(outs[0], xb.grad.cpu()) < FP32_TOL
+
+
 @pytest.mark.parametrize("C,H,W", [(512, 7, 7), (256, 14, 14)], ids=["layer4", "layer3"])
 @pytest.mark.parametrize("R", [1, 2], ids=["3x3", "5x5"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
