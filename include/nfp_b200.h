@@ -70,7 +70,7 @@ enum {
 
 /* which implementation to use */
 enum {
-  NFPB200_PATH_AUTO = 0,    /* fused slab kernels when the problem qualifies, else the generic kernels */
+  NFPB200_PATH_AUTO = 0,    /* fused kernels when the problem qualifies, else the planar, else the generic kernels */
   NFPB200_PATH_GENERIC = 1, /* force the geometry-/measure-generic kernels */
   NFPB200_PATH_FUSED = 2    /* force the fused kernels; NFPB200_EUNSUPPORTED when the problem does not qualify */
 };
@@ -123,10 +123,11 @@ int nfpb200_debug_phase_timing(unsigned long long* device_stamps);
 /* (H', W') = Conv2d output size for the descriptor's geometry; validates the descriptor. */
 int nfpb200_output_shape(const nfpb200_desc_t* desc, int32_t* Ho, int32_t* Wo);
 
-/* Device scratch the given op needs (may be 0).  The caller allocates it and passes it in. */
+/* Device scratch the given op needs (0 for the fused kernels; per-pixel tables for the planar kernels, pair
+ * coefficients for the generic ones).  The caller allocates it and passes it in. */
 int nfpb200_workspace_bytes(const nfpb200_desc_t* desc, int32_t op, size_t* bytes);
 
-/* Writes the name of the kernel path the op would take ("fused/..." or "generic/...") into buf. */
+/* Writes the name of the kernel path the op would take ("fused/...", "planar/..." or "generic/...") into buf. */
 int nfpb200_describe_path(const nfpb200_desc_t* desc, int32_t op, char* buf, size_t buf_bytes);
 
 /* Number of kernel launches the op issues on `stream` (bench.py's gpu_launches). */
