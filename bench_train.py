@@ -103,8 +103,13 @@ def run_gpu(config="eurosat", batch=256, steps=20, warmup=5, amp=True, use_graph
     with torch.cuda.stream(side):
         model = make_model(cfg, dev).to(memory_format=torch.channels_last)
         if world > 1:
-            model = nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], gradient_as_bucket_view=True,
-                                                        bucket_cap_mb=int(os.environ.get("NFP_DDP_BUCKET_MB", "25")))
+            # BatchNorm statistics stay per rank (the reference trains on one GPU), so DDP's per-forward
+            # buffer broadcast is off unless NFP_DDP_BROADCAST_BUFFERS=1
+            model = nn.parallel.DistributedDataParallel(
+                model, device_ids=[dev.index], gradient_as_bucket_view=True,
+                bucket_cap_mb=int(os.environ.get("NFP_DDP_BUCKET_MB", "25")),
+                broadcast_buffers=os.environ.get("NFP_DDP_BROADCAST_BUFFERS", "0") == "1",
+                static_graph=os.environ.get("NFP_DDP_STATIC_GRAPH", "0") == "1")
             if os.environ.get("NFP_DDP_BF16_HOOK", "0") == "1":
                 from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
                 model.register_comm_hook(None, default_hooks.bf16_compress_hook)

@@ -24,6 +24,7 @@ struct StreamArgs {
   int nst;       // ring stages
   int resident;  // backward: the image fits in the ring, pass B re-walks the slots of pass A
   int pad_mode, similarity;
+  int lanech;    // backward: lane-per-channel pass B (C a multiple of 64, chunks a whole number of 64-channel tasks)
   int ggx_tma;   // pooled backward: g_gap_x rows are 16-byte aligned and sized -> fetched with one bulk copy per image
   float eps;
   unsigned long long* dbg;  // optional: 8 globaltimer stamps per CTA (first image), see nfpb200_debug_phase_timing

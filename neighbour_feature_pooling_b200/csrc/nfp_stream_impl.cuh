@@ -46,6 +46,8 @@
 namespace nfp {
 namespace stream {
 
+__host__ __device__ constexpr int align_up(int n, int a) { return (n + a - 1) / a * a; }
+
 template <int H_, int W_, int R_, int TW_>
 struct Cfg {
   static constexpr int H = H_, W = W_, R = R_, TW = TW_;
@@ -63,13 +65,21 @@ struct Cfg {
   static constexpr int HALO = R * W + R;    // elements a strip may read before / after its channel plane
   static constexpr bool PACK = (R == 1 && NSX == 1);  // pass A on packed fp32 pairs where the 96-register budget allows it
   static constexpr int MINB = (R == 1) ? 2 : 1;  // CTAs per SM the register budget is sized for
+  // coefficient table Wd: one row of RS floats per map row (W pixels x KK offsets); padded to whole float4s where a
+  // lane strip is a full row, so the lane-per-channel pass B can fetch a row's coefficients with broadcast LDS.128
+  // (an ODD number of float4s per row: rows start 16-byte aligned and in different banks, so the strip form's
+  // per-lane coefficient loads stay conflict-free; other shapes keep the dense p*KK + o layout)
+  static constexpr bool LANECH = (R == 1 && NSX == 1 && P >= 49);  // shapes with a lane-per-channel pass B (measured: no gain on 2x2)
+  static constexpr int RS4 = align_up(W * KK, 4) / 4;
+  static constexpr int RS = LANECH ? 4 * (RS4 % 2 ? RS4 : RS4 + 1) : W * KK;
+  static constexpr int TASK = 64;                        // its work item: 64 channels = 2 per lane
+  __host__ __device__ static constexpr int widx(int p, int o) { return (p / W) * RS + (p % W) * KK + o; }
   static_assert(W % TW == 0, "strip width must divide W");
   static_assert(HALO * 4 <= 128, "the zeroed lead pad in front of the ring must cover the halo");
   static_assert(NS <= 32 && CPW >= 1 && (CPW & (CPW - 1)) == 0, "channels per group must be a power of two");
 };
 
 // ---- compile-time stencil tables ----------------------------------------------------------------
-__host__ __device__ constexpr int align_up(int n, int a) { return (n + a - 1) / a * a; }
 
 // taps that point outside the map (they fold back onto a window pixel under reflect / replicate padding)
 template <class C>
@@ -221,7 +231,7 @@ struct Smem {
     tfull = take(C::PNV * 4);
     inv = take(C::P * 4);
     rn = take(BWD ? C::P * 4 : 0);
-    wd = take(BWD ? C::P * C::KK * 4 : 0);
+    wd = take(BWD ? C::H * C::RS * 4 : 0);
     gp = take(BWD ? C::P * C::KK * 4 : 0);
     tabs = take(BWD ? Tables<C>::BWD_BYTES : Tables<C>::FWD_BYTES);
     if (BWD) {
@@ -439,7 +449,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
         const int q = (o == C::CTR) ? -1 : (int)qt[idx];
         float v = Gp[idx];
         if (q >= 0) v += Gp[q * KK + (KK - 1 - o)];
-        Wd[idx] = sgn * v;
+        Wd[C::widx(p, o)] = sgn * v;
       }
       // (Wd is next touched after the barriers that follow pass A; Gp is rewritten by the next image after them too)
     }
@@ -647,9 +657,9 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
               const int o = n < C::CTR ? n : n + 1;
               const int q = qt[p * KK + o];
               if (q >= 0) {
-                const float w = Wd[p * KK + o] * (ip * inv[q]);
+                const float w = Wd[C::widx(p, o)] * (ip * inv[q]);
                 const float d = o > C::CTR ? tfull[p * NV + (o - C::CTR)] : tfull[q * NV + (C::CTR - o)];
-                Wd[p * KK + o] = w;
+                Wd[C::widx(p, o)] = w;
                 s = fmaf(w, d, s);
               }
             }
@@ -659,8 +669,8 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 4);
         if (valid && g == 0) {
-          const float sw = 2.f * Wd[p * KK + C::CTR] * (ip * ip);
-          Wd[p * KK + C::CTR] = sw - rn[p] * (s + sw * tfull[p * NV]);
+          const float sw = 2.f * Wd[C::widx(p, C::CTR)] * (ip * ip);
+          Wd[C::widx(p, C::CTR)] = sw - rn[p] * (s + sw * tfull[p * NV]);
         }
       }
       consumer_sync<NT>();
@@ -677,8 +687,94 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
           if (a.ggx_tma) mbar_wait(&gyfull[img & 1], (img >> 1) & 1);  // bulk copy issued by the producer
           ggx = reinterpret_cast<const float*>(smem_raw + L.ggx) + (img & 1) * a.C;
         }
+        bool lanech_done = false;
+        if constexpr (C::LANECH) {
+          if (a.lanech) {
+            // ---- lane-per-channel form: a warp owns a task of 64 channels of the chunk, lane = 2 channels (packed
+            // fp32 pair), and slides a 3-row window down ITS planes: every x element is read from shared memory once
+            // (the strip form reads it three times), the map row's coefficients arrive as broadcast LDS.128, the
+            // results overwrite the plane in place (a plane is private to its lane) and one TMA bulk store per task
+            // writes them back.  Shared-memory wavefronts per image 5152 -> 4024, instructions per channel 31 -> 12.
+            lanech_done = true;
+            const int ntask = CC / C::TASK;
+            const float4* wd4 = reinterpret_cast<const float4*>(Wd);
+            for (int ch = 0; ch < NCH; ++ch) {
+              mbar_wait(&full[slot], ph);
+              unsigned char* sl = ring + slot * L.slot_stride;
+              bool stored = false;
+              for (int t = 0; t < ntask; ++t) {
+                if ((ch * ntask + t) % NW != warp) continue;
+                unsigned char* p0 = sl + (size_t)(t * C::TASK + lane) * P * ESZ;
+                unsigned char* p1 = p0 + 32 * P * ESZ;
+                float g0 = 0.f, g1 = 0.f;
+                if constexpr (MODE == MODE_POOL_BWD) {
+                  g0 = ggx[ch * CC + t * C::TASK + lane] * invP;
+                  g1 = ggx[ch * CC + t * C::TASK + 32 + lane] * invP;
+                }
+                const uint64_t gpair = pack2(g0, g1);
+                uint64_t win[3][W];  // rows rr-1, rr, rr+1 of the two planes (rotating)
+#pragma unroll
+                for (int j = 0; j < W; ++j) {
+                  win[0][j] = 0ull;
+                  win[1][j] = pack2(ldx<T>(p0 + j * ESZ), ldx<T>(p1 + j * ESZ));
+                }
+#pragma unroll
+                for (int rr = 0; rr < C::H; ++rr) {
+                  uint64_t(&up)[W] = win[rr % 3];
+                  uint64_t(&mid)[W] = win[(rr + 1) % 3];
+                  uint64_t(&dn)[W] = win[(rr + 2) % 3];
+#pragma unroll
+                  for (int j = 0; j < W; ++j)
+                    dn[j] = (rr + 1 < C::H) ? pack2(ldx<T>(p0 + ((rr + 1) * W + j) * ESZ), ldx<T>(p1 + ((rr + 1) * W + j) * ESZ))
+                                            : 0ull;
+                  uint64_t out[W];
+#pragma unroll
+                  for (int j = 0; j < W; ++j) out[j] = gpair;
+                  // the row's W*KK coefficients, four at a time (warp-uniform address: one wavefront per load)
+#pragma unroll
+                  for (int q4 = 0; q4 < C::RS4; ++q4) {
+                    const float4 c4 = wd4[rr * (C::RS / 4) + q4];
+                    const float cw[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const int i = q4 * 4 + e;
+                      if (i < W * KK) {
+                        const int j = i / KK, o = i % KK, dy = o / k - R, dx = o % k - R;
+                        if (j + dx >= 0 && j + dx < W) {
+                          const uint64_t xv = dy < 0 ? up[j + dx] : (dy == 0 ? mid[j + dx] : dn[j + dx]);
+                          out[j] = fma2(pack2(cw[e], cw[e]), xv, out[j]);
+                        }
+                      }
+                    }
+                  }
+#pragma unroll
+                  for (int j = 0; j < W; ++j) {
+                    float lo, hi;
+                    unpack2(out[j], lo, hi);
+                    stx<T>(p0 + (rr * W + j) * ESZ, lo);
+                    stx<T>(p1 + (rr * W + j) * ESZ, hi);
+                  }
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  bulk_s2g(gxb + ((size_t)ch * CC + (size_t)t * C::TASK) * P * ESZ, sl + (size_t)t * C::TASK * P * ESZ,
+                           (uint32_t)(C::TASK * P * ESZ));
+                  bulk_commit();
+                }
+                stored = true;
+              }
+              if (stored && lane == 0) bulk_wait_read<0>();  // the slot goes back to the producer: the store has read it
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&empty[slot]);
+              if (++slot == nst) { slot = 0; ph ^= 1; }
+            }
+            NFP_STAMP(3);  // pass B done (this warp)
+          }
+        }
+        if (!lanech_done) {
         int nstore = 0;
-        const float* wdp = Wd + (pos * TW) * KK;
+        const float* wdp = Wd + C::widx(r * W + c0, 0);
         float wr[(R == 1) ? TW : 1][(R == 1) ? KK : 1];
         if constexpr (R == 1) {
 #pragma unroll
@@ -862,6 +958,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
         }
         NFP_STAMP(3);  // pass B done (this warp)
         if (lane == 0) bulk_wait_read<0>();  // staging is part of the union the next image overwrites
+        }
       }
       consumer_sync<NT>();
       if constexpr (MODE == MODE_POOL_BWD) {
@@ -880,7 +977,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
 
 struct Plan {
   bool ok;
-  int CC, NCH, nst, resident, ctas_per_sm;
+  int CC, NCH, nst, resident, ctas_per_sm, lanech;
   size_t smem;
 };
 
@@ -891,7 +988,7 @@ inline int env_int(const char* name, int dflt) {
 
 template <typename T, class C, int MODE>
 Plan plan_for(const KParams& P) {
-  Plan pl{false, 0, 0, 0, 0, 0, 0};
+  Plan pl{false, 0, 0, 0, 0, 0, 0, 0};
   constexpr int esz = (int)sizeof(T);
   constexpr bool bwd = (MODE == MODE_BWD || MODE == MODE_POOL_BWD);
   static const int target_bytes = env_int("NFPB200_CHUNK_BYTES", 16 * 1024);
@@ -901,9 +998,14 @@ Plan plan_for(const KParams& P) {
   if (((size_t)pair * C::P * esz) % 16) return pl;   // TMA bulk store / load granularity
   if (((size_t)C::K * C::P * esz) % 16) return pl;
   if (P.C % pair) return pl;
-  // chunk: the largest CC <= target that divides C and is a whole number of group pairs
+  // backward of the full-row-strip 3x3 shapes: lane-per-channel pass B when C is a whole number of 64-channel tasks
+  // (NFPB200_PASSB_LANECH=0 keeps the strip form for A/B runs)
+  static const int want_lanech = env_int("NFPB200_PASSB_LANECH", 1);
+  pl.lanech = (bwd && C::LANECH && want_lanech && P.C % C::TASK == 0) ? 1 : 0;
+  // chunk: the largest CC <= target that divides C and is a whole number of group pairs (of tasks)
+  const int step = pl.lanech ? C::TASK : pair;
   int best = 0;
-  for (int cc = pair; cc <= P.C; cc += pair) {
+  for (int cc = step; cc <= P.C; cc += step) {
     if (P.C % cc) continue;
     if ((size_t)cc * C::P * esz > (size_t)target_bytes && best) break;
     best = cc;
@@ -939,6 +1041,7 @@ int launch_mode(const KParams& P, StreamArgs a, cudaStream_t stream) {
   a.NCH = pl.NCH;
   a.nst = pl.nst;
   a.resident = pl.resident;
+  a.lanech = pl.lanech;
   auto kern = stream_kernel<T, C, MODE, kNW>;
   // per-device one-time setup (function attributes are per device; a process may drive several GPUs).
   // Idempotent, so a race between two host threads doing it at once is harmless.
