@@ -69,7 +69,7 @@ struct Cfg {
   // lane strip is a full row, so the lane-per-channel pass B can fetch a row's coefficients with broadcast LDS.128
   // (an ODD number of float4s per row: rows start 16-byte aligned and in different banks, so the strip form's
   // per-lane coefficient loads stay conflict-free; other shapes keep the dense p*KK + o layout)
-  static constexpr bool LANECH = (R == 1 && NSX == 1 && P >= 49);  // shapes with a lane-per-channel pass B (measured: no gain on 2x2)
+  static constexpr bool LANECH = (NSX == 1 && P >= 49);  // shapes with a lane-per-channel pass B (measured: no gain on 2x2)
   static constexpr int RS4 = align_up(W * KK, 4) / 4;
   static constexpr int RS = LANECH ? 4 * (RS4 % 2 ? RS4 : RS4 + 1) : W * KK;
   static constexpr int TASK = 64;                        // its work item: 64 channels = 2 per lane
@@ -691,8 +691,8 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
         if constexpr (C::LANECH) {
           if (a.lanech) {
             // ---- lane-per-channel form: a warp owns a task of 64 channels of the chunk, lane = 2 channels (packed
-            // fp32 pair), and slides a 3-row window down ITS planes: every x element is read from shared memory once
-            // (the strip form reads it three times), the map row's coefficients arrive as broadcast LDS.128, the
+            // fp32 pair), and slides a k-row window down ITS planes: every x element is read from shared memory once
+            // (the strip form reads it k times), the map row's coefficients arrive as broadcast LDS.128, the
             // results overwrite the plane in place (a plane is private to its lane) and one TMA bulk store per task
             // writes them back.  Shared-memory wavefronts per image 5152 -> 4024, instructions per channel 31 -> 12.
             lanech_done = true;
@@ -712,21 +712,22 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
                   g1 = ggx[ch * CC + t * C::TASK + 32 + lane] * invP;
                 }
                 const uint64_t gpair = pack2(g0, g1);
-                uint64_t win[3][W];  // rows rr-1, rr, rr+1 of the two planes (rotating)
+                // rows rr-R .. rr+R of the two planes, rotating: map row q lives in win[q mod k]; rows outside the
+                // map are zero
+                uint64_t win[k][W];
 #pragma unroll
-                for (int j = 0; j < W; ++j) {
-                  win[0][j] = 0ull;
-                  win[1][j] = pack2(ldx<T>(p0 + j * ESZ), ldx<T>(p1 + j * ESZ));
-                }
-#pragma unroll
-                for (int rr = 0; rr < C::H; ++rr) {
-                  uint64_t(&up)[W] = win[rr % 3];
-                  uint64_t(&mid)[W] = win[(rr + 1) % 3];
-                  uint64_t(&dn)[W] = win[(rr + 2) % 3];
+                for (int q = 0; q < k; ++q)
 #pragma unroll
                   for (int j = 0; j < W; ++j)
-                    dn[j] = (rr + 1 < C::H) ? pack2(ldx<T>(p0 + ((rr + 1) * W + j) * ESZ), ldx<T>(p1 + ((rr + 1) * W + j) * ESZ))
-                                            : 0ull;
+                    win[q][j] = (q < R && q < C::H) ? pack2(ldx<T>(p0 + (q * W + j) * ESZ), ldx<T>(p1 + (q * W + j) * ESZ))
+                                                    : 0ull;
+#pragma unroll
+                for (int rr = 0; rr < C::H; ++rr) {
+#pragma unroll
+                  for (int j = 0; j < W; ++j)
+                    win[(rr + R) % k][j] = (rr + R < C::H) ? pack2(ldx<T>(p0 + ((rr + R) * W + j) * ESZ),
+                                                                   ldx<T>(p1 + ((rr + R) * W + j) * ESZ))
+                                                           : 0ull;
                   uint64_t out[W];
 #pragma unroll
                   for (int j = 0; j < W; ++j) out[j] = gpair;
@@ -740,10 +741,8 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
                       const int i = q4 * 4 + e;
                       if (i < W * KK) {
                         const int j = i / KK, o = i % KK, dy = o / k - R, dx = o % k - R;
-                        if (j + dx >= 0 && j + dx < W) {
-                          const uint64_t xv = dy < 0 ? up[j + dx] : (dy == 0 ? mid[j + dx] : dn[j + dx]);
-                          out[j] = fma2(pack2(cw[e], cw[e]), xv, out[j]);
-                        }
+                        if (j + dx >= 0 && j + dx < W && rr + dy >= 0 && rr + dy < C::H)
+                          out[j] = fma2(pack2(cw[e], cw[e]), win[(rr + dy + k) % k][j + dx], out[j]);
                       }
                     }
                   }
