@@ -15,12 +15,18 @@
 //   forward  y = dot / (max(|p|,eps) max(|q|,eps)) for the K taps -> the only HBM write;
 //            pooled mode reduces y and x over the plane instead (nfp_pooling head).
 //   backward the table + gy become a per-pixel k x k stencil of coefficients Wd[p][o] (closed form
-//            of ATen's cosine_similarity backward; gather form, no atomics); then
+//            of ATen's cosine_similarity backward; gather form, no atomics): the gy-only part
+//            S[p][o] is built from compile-time fold tables before pass A (behind the first loads), then
+//            closed with the inverse norms after it; then
 //   pass B   gx[c][p] = sum_o Wd[p][o] * x[c][p+o], chunk by chunk.  If the whole image fits in
 //            the ring ("resident") the chunks of pass A are still there; otherwise the producer
 //            streams them a second time -- they were read microseconds ago by the same SM, so
-//            the second read is served by the 126 MB L2, not by HBM.  Each warp stages its planes
-//            in shared memory and writes them back with TMA bulk stores.
+//            the second read is served by the 126 MB L2, not by HBM.  Two forms:
+//            lane-per-channel (7x7 maps, C % 64 == 0): a warp owns 64 channels, a lane slides a k-row
+//            window down its own two planes (each x element read from shared memory once, coefficients
+//            as broadcast LDS.128, FFMA2), results in place, one TMA bulk store per task;
+//            strip (everything else): lane = (row strip, channel slot), coefficients in registers,
+//            results staged per warp and written with TMA bulk stores.
 //
 // The index arithmetic of the stencil (reflect / replicate / zero padding, tap order of
 // nfp.py:64-67) is evaluated at COMPILE time into __device__ const tables.
