@@ -75,6 +75,13 @@ enum {
   NFPB200_PATH_FUSED = 2    /* force the fused kernels; NFPB200_EUNSUPPORTED when the problem does not qualify */
 };
 
+/* Optional hint, OR-ed into nfpb200_desc_t.path, for nfpb200_backward / nfpb200_pool_backward: `x` was NOT written by
+ * the kernel that precedes this call on the stream (it is a saved forward activation, as under autograd).  The fused
+ * backward kernels are launched with programmatic dependent launch; with the hint they start streaming x while the
+ * preceding NFP kernel is still draining and only wait for it before touching the upstream gradient and gx.  Never
+ * set it when x may be an output of the immediately preceding NFP launch (e.g. stacked NFP layers' forward). */
+#define NFPB200_HINT_X_STABLE 0x100
+
 /* operations, for nfpb200_workspace_bytes / nfpb200_describe_path */
 enum { NFPB200_OP_FORWARD = 0, NFPB200_OP_BACKWARD = 1, NFPB200_OP_POOL_FORWARD = 2, NFPB200_OP_POOL_BACKWARD = 3 };
 
@@ -106,7 +113,7 @@ typedef struct nfpb200_desc {
   float eps;                /* nfp.py:33 */
   float p;                  /* nfp.py:30: ord of NORM (INFINITY allowed), exponent of SCS */
   float q_scs;              /* nfp.py:34 */
-  int32_t path;             /* NFPB200_PATH_* */
+  int32_t path;             /* NFPB200_PATH_* [| NFPB200_HINT_X_STABLE] */
 } nfpb200_desc_t;
 
 int nfpb200_abi_version(void);

@@ -26,6 +26,7 @@ MEASURES = {
     "sharpened_cosine": 16,  # nfp.py:117 accepts both spellings
 }
 PATHS = {"auto": 0, "generic": 1, "fused": 2}
+HINT_X_STABLE = 0x100   # NFPB200_HINT_X_STABLE, OR-ed into Desc.path for the backward entry points
 OP_FORWARD, OP_BACKWARD, OP_POOL_FORWARD, OP_POOL_BACKWARD = 0, 1, 2, 3
 
 EXPORTS = (

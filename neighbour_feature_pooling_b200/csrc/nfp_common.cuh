@@ -20,6 +20,7 @@ struct KParams {
   int stride, pad, dil, mode;
   int Ho, Wo;
   int similarity, diff_taps, pkind;
+  int x_stable;         // NFPB200_HINT_X_STABLE: x is not an output of the launch that precedes this one
   float eps, p, q;
 };
 

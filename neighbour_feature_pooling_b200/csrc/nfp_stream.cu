@@ -54,6 +54,7 @@ int stream_forward(const KParams& P, int dtype, const void* x, void* y, const La
 int stream_backward(const KParams& P, int dtype, const void* x, const void* gy, void* gx, const LaunchCtx& ctx) {
   stream::StreamArgs a{};
   a.x = x; a.gy = gy; a.gx = gx;
+  a.x_early = P.x_stable;
   return run(P, dtype, stream::MODE_BWD, a, ctx.stream);
 }
 int stream_pool_forward(const KParams& P, int dtype, const void* x, float* gap_x, float* gap_nfp,
@@ -66,6 +67,7 @@ int stream_pool_backward(const KParams& P, int dtype, const void* x, const float
                          void* gx, const LaunchCtx& ctx) {
   stream::StreamArgs a{};
   a.x = x; a.g_gap_x = g_gap_x; a.g_gap_nfp = g_gap_nfp; a.gx = gx;
+  a.x_early = P.x_stable;
   a.ggx_tma = (P.C % 4 == 0) && (reinterpret_cast<uintptr_t>(g_gap_x) % 16 == 0);
   return run(P, dtype, stream::MODE_POOL_BWD, a, ctx.stream);
 }

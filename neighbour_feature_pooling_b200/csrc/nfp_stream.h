@@ -25,6 +25,7 @@ struct StreamArgs {
   int resident;  // backward: the image fits in the ring, pass B re-walks the slots of pass A
   int pad_mode, similarity;
   int lanech;    // backward: lane-per-channel pass B (C a multiple of 64, chunks a whole number of 64-channel tasks)
+  int x_early;   // backward: x is stable across the preceding launch -> stream it before griddepcontrol.wait
   int ggx_tma;   // pooled backward: g_gap_x rows are 16-byte aligned and sized -> fetched with one bulk copy per image
   float eps;
   unsigned long long* dbg;  // optional: 8 globaltimer stamps per CTA (first image), see nfpb200_debug_phase_timing

@@ -332,11 +332,14 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
       bulk_g2s(smem_raw + L.tabs, reinterpret_cast<const unsigned char*>(gt) + (BWD ? Tables<C>::BWD_OFFSET : 0),
                TAB_BYTES, tabfull);
       grid_launch_dependents();  // PDL: the next grid may be scheduled as SM resources free up
-      grid_dependency_wait();    // PDL: x / gy are produced by the preceding grid
+      // PDL: the upstream gradient (and, without the x-stable hint, x) is produced by the preceding grid.  With the
+      // hint the first image's x chunks go out first (a ring-full of them), the wait comes before its gradient loads.
+      bool dep_pending = BWD && a.x_early;
+      if (!dep_pending) grid_dependency_wait();
       int slot = 0, img = 0;
       uint32_t ph = 0;
       const int npass = (BWD && !resident) ? 2 : 1;
-      for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++img) {
+      auto load_grads = [&](int b, int img) {
         if (MODE == MODE_BWD) {
           const int par = img & 1;
           mbar_wait(&gyempty[par], ((img >> 1) & 1) ^ 1);
@@ -344,22 +347,35 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
           bulk_g2s(smem_raw + L.gyraw + par * GY_STRIDE, reinterpret_cast<const T*>(a.gy) + (size_t)b * K * P,
                    (uint32_t)GY_BYTES, &gyfull[par]);
         }
-
         if (MODE == MODE_POOL_BWD && a.ggx_tma) {  // the image's d out / d GAP(x): C floats, one bulk copy
           const int par = img & 1;
           mbar_wait(&gyempty[par], ((img >> 1) & 1) ^ 1);
           mbar_expect_tx(&gyfull[par], (uint32_t)a.C * 4u);
           bulk_g2s(smem_raw + L.ggx + par * a.C * 4, a.g_gap_x + (size_t)b * a.C, (uint32_t)a.C * 4u, &gyfull[par]);
         }
+      };
+      for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++img) {
+        if (!dep_pending) load_grads(b, img);
         const unsigned char* xb = reinterpret_cast<const unsigned char*>(a.x) + (size_t)b * a.C * P * ESZ;
+        int issued = 0;
         for (int pass = 0; pass < npass; ++pass) {
           const unsigned char* src = xb;
-          for (int ch = 0; ch < NCH; ++ch, src += chunk_bytes) {
+          for (int ch = 0; ch < NCH; ++ch, src += chunk_bytes, ++issued) {
+            if (dep_pending && issued == nst) {  // the ring is full of the first image's x: now wait, then its gradients
+              grid_dependency_wait();
+              dep_pending = false;
+              load_grads(b, img);
+            }
             mbar_wait(&empty[slot], ph ^ 1);
             mbar_expect_tx(&full[slot], chunk_bytes);
             bulk_g2s(ring + slot * L.slot_stride, src, chunk_bytes, &full[slot]);
             if (++slot == nst) { slot = 0; ph ^= 1; }
           }
+        }
+        if (dep_pending) {  // fewer chunks than ring stages
+          grid_dependency_wait();
+          dep_pending = false;
+          load_grads(b, img);
         }
       }
     }
@@ -379,7 +395,10 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
       for (int i = tid; i < pad_words; i += NT) zp[i] = 0u;
     }
   }
-  grid_dependency_wait();  // PDL: nothing below may touch global memory the preceding grid still uses
+  // PDL: nothing below may touch global memory the preceding grid still uses -- except, with the x-stable hint, the
+  // ring (x only): then pass A of the first image runs first and the wait comes right after it
+  const bool x_early = BWD && a.x_early;
+  if (!x_early) grid_dependency_wait();
   consumer_sync<NT>();
 
   const float sgn = a.similarity ? 1.f : -1.f;
@@ -399,9 +418,11 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
     const int slot0 = slot;
     const uint32_t ph0 = ph;
 
-    // ---- backward, before pass A (overlaps the latency of the first chunk loads): the gy-only part of the
+    // ---- backward, before pass A (overlaps the latency of the first chunk loads) or, with the x-stable hint,
+    // right after it (pass A overlaps the tail of the preceding launch instead): the gy-only part of the
     // stencil, S[p][o] = sum of G over the taps of p that land on q = p + off(o), plus the taps of q that land on p
     // (o == ctr: the taps of p that land on p itself, replicate padding).  Gather form: no atomics, fixed order.
+    auto stencil_part = [&]() {
     if constexpr (BWD) {
       const int16_t* qt = reinterpret_cast<const int16_t*>(smem_raw + L.t_q);
       const int16_t* fsrc = reinterpret_cast<const int16_t*>(smem_raw + L.t_fsrc);
@@ -459,6 +480,8 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
       }
       // (Wd is next touched after the barriers that follow pass A; Gp is rewritten by the next image after them too)
     }
+    };
+    if (!x_early) stencil_part();
 
     // ---- pass A: per-pixel |x|^2 and forward-direction dots, streamed over the chunks -----------
     {
@@ -592,6 +615,10 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
       }
     }
     NFP_STAMP(1);  // pass A done (this warp)
+    if (x_early) {
+      if (img == 0) grid_dependency_wait();
+      stencil_part();
+    }
     consumer_sync<NT>();
     if constexpr (!BWD) {
       if (img == 0) mbar_wait(tabfull, 0);  // stencil tables (fetched by the producer at kernel start)

@@ -154,6 +154,9 @@ class _NFPSimilarity(torch.autograd.Function):
     def backward(ctx, gy):
         (x,) = ctx.saved_tensors
         desc = _desc_for(x, ctx.cfg)
+        # x is a saved forward activation: whatever NFP kernel precedes this launch on the stream did not write it,
+        # so the fused backward may stream it while that kernel drains (NFPB200_HINT_X_STABLE, include/nfp_b200.h)
+        desc.path |= _capi.HINT_X_STABLE
         gy = gy.to(x.dtype).contiguous()
         if gy.data_ptr() % 16:
             gy = gy.clone()
@@ -187,6 +190,9 @@ class _NFPGapPair(torch.autograd.Function):
     def backward(ctx, g_gap_x, g_gap_nfp):
         (x,) = ctx.saved_tensors
         desc = _desc_for(x, ctx.cfg)
+        # x is a saved forward activation: whatever NFP kernel precedes this launch on the stream did not write it,
+        # so the fused backward may stream it while that kernel drains (NFPB200_HINT_X_STABLE, include/nfp_b200.h)
+        desc.path |= _capi.HINT_X_STABLE
         g_gap_x = g_gap_x.float().contiguous()
         g_gap_nfp = g_gap_nfp.float().contiguous()
         gx = torch.empty_like(x)

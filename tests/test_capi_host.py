@@ -90,6 +90,14 @@ def test_path_selection_and_workspace():
     assert _capi.launch_count(planar, _capi.OP_FORWARD) == 2 and _capi.launch_count(planar, _capi.OP_BACKWARD) == 3
     assert _capi.describe_path(planar, _capi.OP_POOL_FORWARD) == "generic/pairs"  # pooled mode: generic kernels
     assert _capi.describe_path(_desc(B=2, C=16, H=112, W=112, path="generic"), _capi.OP_FORWARD) == "generic/pairs"
+    # the x-stable hint rides on `path` and changes neither the path choice nor the workspace; other bits are refused
+    hinted = _desc(B=256, C=512)
+    hinted.path |= _capi.HINT_X_STABLE
+    assert _capi.describe_path(hinted, _capi.OP_BACKWARD) == _capi.describe_path(fused, _capi.OP_BACKWARD)
+    assert _capi.workspace_bytes(hinted, _capi.OP_BACKWARD) == 0
+    bad = _desc(B=256, C=512)
+    bad.path |= 0x200
+    assert _capi.load().nfpb200_workspace_bytes(ctypes.byref(bad), _capi.OP_BACKWARD, ctypes.byref(n)) == -1
     # every measure has a generic path
     for m in _capi.MEASURES:
         assert _capi.describe_path(_desc(measure=m, path="generic"), _capi.OP_BACKWARD) == "generic/pairs"

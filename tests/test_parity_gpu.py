@@ -265,6 +265,48 @@ def test_pooled_head_equals_map_then_gap(shape, cuda_device):
     assert rel_err(xa.grad.cpu(), xb.grad.cpu()) < FP32_TOL
 
 
+@pytest.mark.parametrize("shape", [(256, 512, 7, 7, 1), (700, 64, 7, 7, 1), (64, 256, 14, 14, 1), (40, 128, 7, 7, 2),
+                                   (96, 24, 7, 7, 1)], ids=lambda s: "x".join(map(str, s[:4])) + f"_r{s[4]}")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_backward_x_stable_hint_same_bits(shape, dtype, cuda_device):
+    """NFPB200_HINT_X_STABLE lets the fused backward stream x while the preceding NFP launch drains (PDL) and moves
+    the gy-only stencil part behind pass A; in chains of NFP launches the results are bit-identical to the
+    conservative order, for every launch of the chain."""
+    import ctypes
+    from neighbour_feature_pooling_b200 import _capi
+    B, C, H, W, R = shape
+    K = (2 * R + 1) ** 2 - 1
+    gen = torch.Generator().manual_seed(17)
+    kd = _capi.F32 if dtype == torch.float32 else _capi.BF16
+    xs = [torch.randn(B, C, H, W, generator=gen).to(cuda_device, dtype) for _ in range(3)]
+    gys = [torch.randn(B, K, H, W, generator=gen).to(cuda_device, dtype) for _ in range(3)]
+    lib = _capi.load()
+    st = torch.cuda.current_stream().cuda_stream
+    res = {}
+    for hint in (0, _capi.HINT_X_STABLE):
+        desc = _capi.make_desc(kd, B, C, H, W, R, 1, R, 1, "reflect", "cosine", True, False, 1e-6, 1, 1e-6, "auto")
+        fdesc = _capi.make_desc(kd, B, C, H, W, R, 1, R, 1, "reflect", "cosine", True, False, 1e-6, 1, 1e-6, "auto")
+        desc.path |= hint
+        ys = [torch.empty_like(g) for g in gys]
+        gxs = [torch.empty_like(x) for x in xs]
+        for rep in range(2):
+            for i in range(3):   # forward, backward, backward of the next buffer ... back to back on one stream
+                _capi.check(lib.nfpb200_forward(ctypes.byref(fdesc), xs[i].data_ptr(), ys[i].data_ptr(), None, 0, st), "fwd")
+                _capi.check(lib.nfpb200_backward(ctypes.byref(desc), xs[i].data_ptr(), gys[i].data_ptr(),
+                                                 gxs[i].data_ptr(), None, 0, st), "bwd")
+                j = (i + 1) % 3
+                _capi.check(lib.nfpb200_backward(ctypes.byref(desc), xs[j].data_ptr(), gys[j].data_ptr(),
+                                                 gxs[j].data_ptr(), None, 0, st), "bwd")
+        torch.cuda.synchronize()
+        res[hint] = [t.float().cpu() for t in ys + gxs]
+    assert all(torch.equal(a, b) for a, b in zip(res[0], res[_capi.HINT_X_STABLE]))
+    y_ref, gx_ref = O.nfp_forward_backward(xs[0][-2:].double().cpu(), gys[0][-2:].double().cpu(), R=R, measure="cosine",
+                                           padding=R)
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert rel_err(res[_capi.HINT_X_STABLE][0][-2:], y_ref) < tol
+    assert rel_err(res[_capi.HINT_X_STABLE][3][-2:], gx_ref) < tol
+
+
 @pytest.mark.parametrize("shape", [(5, 64, 7, 7), (300, 16, 7, 7), (3, 6, 14, 14)], ids=lambda s: "x".join(map(str, s)))
 def test_pool_backward_gradient_row_alignment(shape, cuda_device):
     """nfpb200_pool_backward stages d out / d GAP(x) with one TMA bulk copy per image when its rows are 16-byte
