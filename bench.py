@@ -210,6 +210,17 @@ class LayerBench:
         self.fwd(i)
         self.bwd(i)
 
+    def bwd_conservative(self, i):   # without NFPB200_HINT_X_STABLE: the backward waits for the preceding launch first
+        s = torch.cuda.current_stream(self.dev).cuda_stream
+        rc = self.lib.nfpb200_backward(ctypes.byref(self.desc), self.x[i].data_ptr(), self.gy[i].data_ptr(),
+                                       self.gx[i].data_ptr(), self.ws.data_ptr() if self.ws_n else None,
+                                       self.ws_n, s)
+        self.capi.check(rc, "nfpb200_backward")
+
+    def step_conservative(self, i):
+        self.fwd(i)
+        self.bwd_conservative(i)
+
     # pooled mode (the nfp_pooling head, models/NFP_Pooling.py:25-36): GAP(x) and GAP(NFP(x)) from one pass over x,
     # backward from their two gradients; the similarity map is never written
     def pool_setup(self):
@@ -523,6 +534,10 @@ def main():
     t_fwd = lb.timed(lb.fwd, args.steps, args.warmup, sampler, sampler_tag) / args.steps
     t_bwd = lb.timed(lb.bwd, args.steps, args.warmup, sampler, sampler_tag) / args.steps
     fwd_bytes, bwd_bytes = algorithmic_bytes(B, C, H, W, R, lb.esz)
+    # the same without the x-stable hint (a backward that may not touch x before the preceding launch has finished)
+    n_cons = min(args.steps, 300)
+    t_step_cons = lb.timed(lb.step_conservative, n_cons, 5, sampler, "kernels") / n_cons
+    t_bwd_cons = lb.timed(lb.bwd_conservative, n_cons, 5, sampler, "kernels") / n_cons
     # ---- e2e through the nn.Module API with host buffers ------------------------------------------------
     e2e_steps = min(args.steps, 50)
     t_e2e, h2d, d2h, _chk = e2e_through_module(dev, B, C, H, W, R, args.dtype, e2e_steps, min(args.warmup, 5),
@@ -616,6 +631,13 @@ def main():
                               "frac": (fwd_bytes + bwd_bytes) * args.steps / t_step_total / 1e9 / hbm_peak,
                               "bytes_per_step": fwd_bytes + bwd_bytes,
                               "bwd_share_of_step": t_bwd / (t_fwd + t_bwd)},
+            "without_x_stable_hint": {"us_per_step": t_step_cons * 1e6, "us_bwd": t_bwd_cons * 1e6,
+                                      "maps_per_s": world * B / t_step_cons,
+                                      "step_frac": (fwd_bytes + bwd_bytes) / t_step_cons / 1e9 / hbm_peak,
+                                      "bwd_frac": bwd_bytes / t_bwd_cons / 1e9 / hbm_peak,
+                                      "note": "NFPB200_HINT_X_STABLE (include/nfp_b200.h) lets a fused backward stream x "
+                                              "while the preceding NFP launch drains; it only matters when NFP launches "
+                                              "are adjacent on the stream, as in this microbenchmark"},
             "clocks": sampler.summary(),
         }
         if cpu is not None:

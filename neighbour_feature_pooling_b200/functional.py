@@ -14,6 +14,7 @@ CPU tensors are rejected (except the constructor-time shape probes described in
 from __future__ import annotations
 
 import ctypes
+import os
 import math
 from dataclasses import dataclass, replace
 
@@ -92,6 +93,7 @@ def _reject_cpu(x: torch.Tensor):
 
 
 _KERNEL_DTYPES = {torch.float32: _capi.F32, torch.bfloat16: _capi.BF16}
+_X_STABLE_HINT = os.environ.get("NFPB200_X_STABLE_HINT", "1") != "0"
 
 
 def _prepare(x: torch.Tensor):
@@ -155,8 +157,11 @@ class _NFPSimilarity(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         desc = _desc_for(x, ctx.cfg)
         # x is a saved forward activation: whatever NFP kernel precedes this launch on the stream did not write it,
-        # so the fused backward may stream it while that kernel drains (NFPB200_HINT_X_STABLE, include/nfp_b200.h)
-        desc.path |= _capi.HINT_X_STABLE
+        # so the fused backward may stream it while that kernel drains (NFPB200_HINT_X_STABLE, include/nfp_b200.h).
+        # It pays when NFP launches are adjacent on the stream (-1.7 us per backward); after any other kernel there is
+        # nothing to overlap and the reordered prologue costs ~0.9 us.  NFPB200_X_STABLE_HINT=0 switches it off.
+        if _X_STABLE_HINT:
+            desc.path |= _capi.HINT_X_STABLE
         gy = gy.to(x.dtype).contiguous()
         if gy.data_ptr() % 16:
             gy = gy.clone()
@@ -191,8 +196,11 @@ class _NFPGapPair(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         desc = _desc_for(x, ctx.cfg)
         # x is a saved forward activation: whatever NFP kernel precedes this launch on the stream did not write it,
-        # so the fused backward may stream it while that kernel drains (NFPB200_HINT_X_STABLE, include/nfp_b200.h)
-        desc.path |= _capi.HINT_X_STABLE
+        # so the fused backward may stream it while that kernel drains (NFPB200_HINT_X_STABLE, include/nfp_b200.h).
+        # It pays when NFP launches are adjacent on the stream (-1.7 us per backward); after any other kernel there is
+        # nothing to overlap and the reordered prologue costs ~0.9 us.  NFPB200_X_STABLE_HINT=0 switches it off.
+        if _X_STABLE_HINT:
+            desc.path |= _capi.HINT_X_STABLE
         g_gap_x = g_gap_x.float().contiguous()
         g_gap_nfp = g_gap_nfp.float().contiguous()
         gx = torch.empty_like(x)
