@@ -49,16 +49,9 @@ int make_params(const nfpb200_desc_t* d, KParams* out) {
   return NFPB200_OK;
 }
 
-// 3 = planar, 2 = fused/stream, 1 = fused/slab, 0 = generic, <0 = error
+// 3 = planar, 2 = fused (cluster-split or streaming-ring kernels), 0 = generic, <0 = error
 int choose_path(const nfpb200_desc_t* d, const KParams& P, int op) {
-  // NFPB200_FUSED_IMPL=slab selects the first-generation slab kernels (A/B comparisons)
-  static const bool prefer_slab = [] {
-    const char* e = getenv("NFPB200_FUSED_IMPL");
-    return e && strcmp(e, "slab") == 0;
-  }();
-  const bool can_stream = !prefer_slab && stream_supported(P, d->dtype, d->measure, op);
-  const bool can_slab = fused_supported(P, d->dtype, d->measure, op);
-  const int fused = can_stream ? 2 : (can_slab ? 1 : 0);
+  const int fused = stream_supported(P, d->dtype, d->measure, op) ? 2 : 0;
   const int want = d->path & ~NFPB200_HINT_X_STABLE;
   if (want == NFPB200_PATH_FUSED) return fused ? fused : NFPB200_EUNSUPPORTED;
   if (want == NFPB200_PATH_GENERIC) return 0;
@@ -141,8 +134,7 @@ int nfpb200_describe_path(const nfpb200_desc_t* desc, int32_t op, char* buf, siz
   if (path < 0) return path;
   snprintf(buf, buf_bytes, "%s",
            path == 3 ? planar_name(P, desc->dtype, op)
-                     : (path == 2 ? stream_name(P, desc->dtype, desc->measure, op)
-                                  : (path == 1 ? fused_name(P, desc->dtype, desc->measure, op) : "generic/pairs")));
+                     : (path == 2 ? stream_name(P, desc->dtype, desc->measure, op) : "generic/pairs"));
   return NFPB200_OK;
 }
 
@@ -178,7 +170,7 @@ int nfpb200_forward(const nfpb200_desc_t* desc, const void* x, void* y, void* wo
   NFP_PROLOGUE(NFPB200_OP_FORWARD)
   if (path == 3) return planar_forward(P, desc->dtype, x, y, ctx);
   if (path == 2) return stream_forward(P, desc->dtype, x, y, ctx);
-  return path ? fused_forward(P, desc->dtype, x, y, ctx) : generic_forward(P, desc->dtype, desc->measure, x, y, ctx);
+  return generic_forward(P, desc->dtype, desc->measure, x, y, ctx);
 }
 
 int nfpb200_backward(const nfpb200_desc_t* desc, const void* x, const void* gy, void* gx, void* workspace,
@@ -188,8 +180,7 @@ int nfpb200_backward(const nfpb200_desc_t* desc, const void* x, const void* gy, 
   NFP_PROLOGUE(NFPB200_OP_BACKWARD)
   if (path == 3) return planar_backward(P, desc->dtype, x, gy, gx, ctx);
   if (path == 2) return stream_backward(P, desc->dtype, x, gy, gx, ctx);
-  return path ? fused_backward(P, desc->dtype, x, gy, gx, ctx)
-              : generic_backward(P, desc->dtype, desc->measure, x, gy, gx, ctx);
+  return generic_backward(P, desc->dtype, desc->measure, x, gy, gx, ctx);
 }
 
 int nfpb200_pool_forward(const nfpb200_desc_t* desc, const void* x, float* gap_x, float* gap_nfp, void* workspace,
@@ -198,8 +189,7 @@ int nfpb200_pool_forward(const nfpb200_desc_t* desc, const void* x, float* gap_x
   if (misaligned(x)) return NFPB200_EALIGN;
   NFP_PROLOGUE(NFPB200_OP_POOL_FORWARD)
   if (path == 2) return stream_pool_forward(P, desc->dtype, x, gap_x, gap_nfp, ctx);
-  return path ? fused_pool_forward(P, desc->dtype, x, gap_x, gap_nfp, ctx)
-              : generic_pool_forward(P, desc->dtype, desc->measure, x, gap_x, gap_nfp, ctx);
+  return generic_pool_forward(P, desc->dtype, desc->measure, x, gap_x, gap_nfp, ctx);
 }
 
 int nfpb200_pool_backward(const nfpb200_desc_t* desc, const void* x, const float* g_gap_x, const float* g_gap_nfp,
@@ -208,8 +198,7 @@ int nfpb200_pool_backward(const nfpb200_desc_t* desc, const void* x, const float
   if (misaligned(x) || misaligned(gx)) return NFPB200_EALIGN;
   NFP_PROLOGUE(NFPB200_OP_POOL_BACKWARD)
   if (path == 2) return stream_pool_backward(P, desc->dtype, x, g_gap_x, g_gap_nfp, gx, ctx);
-  return path ? fused_pool_backward(P, desc->dtype, x, g_gap_x, g_gap_nfp, gx, ctx)
-              : generic_pool_backward(P, desc->dtype, desc->measure, x, g_gap_x, g_gap_nfp, gx, ctx);
+  return generic_pool_backward(P, desc->dtype, desc->measure, x, g_gap_x, g_gap_nfp, gx, ctx);
 }
 
 }  // extern "C"

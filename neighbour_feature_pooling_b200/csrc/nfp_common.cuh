@@ -72,19 +72,7 @@ int generic_pool_forward(const KParams& P, int dtype, int measure, const void* x
 int generic_pool_backward(const KParams& P, int dtype, int measure, const void* x, const float* g_gap_x,
                           const float* g_gap_nfp, void* gx, const LaunchCtx& ctx);
 
-// fused slab kernels (cosine, stride 1, dilation 1, pad = R): nfp_fused.cu
-bool fused_supported(const KParams& P, int dtype, int measure, int op);
-const char* fused_name(const KParams& P, int dtype, int measure, int op);
-size_t fused_workspace_bytes(const KParams& P, int dtype, int measure, int op);
-int fused_launch_count(const KParams& P, int dtype, int measure, int op);
-int fused_forward(const KParams& P, int dtype, const void* x, void* y, const LaunchCtx& ctx);
-int fused_backward(const KParams& P, int dtype, const void* x, const void* gy, void* gx, const LaunchCtx& ctx);
-int fused_pool_forward(const KParams& P, int dtype, const void* x, float* gap_x, float* gap_nfp,
-                       const LaunchCtx& ctx);
-int fused_pool_backward(const KParams& P, int dtype, const void* x, const float* g_gap_x, const float* g_gap_nfp,
-                        void* gx, const LaunchCtx& ctx);
-
-// streaming fused kernels (same coverage as the slab kernels, persistent TMA pipeline): nfp_stream.cu
+// fused kernels (cosine, stride 1, dilation 1, pad = R; cluster-split and streaming-ring forms): nfp_stream.cu
 bool stream_supported(const KParams& P, int dtype, int measure, int op);
 const char* stream_name(const KParams& P, int dtype, int measure, int op);
 int stream_forward(const KParams& P, int dtype, const void* x, void* y, const LaunchCtx& ctx);

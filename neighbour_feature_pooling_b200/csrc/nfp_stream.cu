@@ -1,5 +1,9 @@
 // Dispatcher of the streaming fused NFP kernels: geometry check, dtype selection, entry points used
 // by the C ABI (nfp_capi.cu).  The kernels themselves live in nfp_stream_impl.cuh.
+#include <stdlib.h>
+#include <string.h>
+
+#include "nfp_split.h"
 #include "nfp_stream.h"
 
 namespace nfp {
@@ -22,7 +26,28 @@ int op_mode(int op) {
   }
 }
 
+// the cluster-split kernels (nfp_split_impl.cuh) take every problem their planner accepts; the one-CTA-per-image
+// ring kernels (nfp_stream_impl.cuh) remain for the rest and for A/B runs (NFPB200_FUSED_IMPL=stream)
+bool split_ok(const KParams& P, int dtype, int mode) {
+  static const bool want_split = [] {
+    const char* e = getenv("NFPB200_FUSED_IMPL");
+    return e && strcmp(e, "split") == 0;
+  }();
+  if (!want_split) return false;
+  return (dtype == NFPB200_BF16 ? split::plan_bf16(P, mode) : split::plan_f32(P, mode)).ok;
+}
+
 int run(const KParams& P, int dtype, int mode, stream::StreamArgs a, cudaStream_t s) {
+  if (split_ok(P, dtype, mode)) {
+    split::SplitArgs sa{};
+    sa.x = a.x; sa.gy = a.gy; sa.y = a.y; sa.gx = a.gx;
+    sa.g_gap_x = a.g_gap_x; sa.g_gap_nfp = a.g_gap_nfp; sa.gap_x = a.gap_x; sa.gap_nfp = a.gap_nfp;
+    sa.B = P.B; sa.C = P.C;
+    sa.pad_mode = P.mode; sa.similarity = P.similarity; sa.eps = P.eps;
+    sa.x_early = a.x_early;
+    sa.dbg = stream::g_debug_stamps;
+    return dtype == NFPB200_BF16 ? split::launch_bf16(P, mode, sa, s) : split::launch_f32(P, mode, sa, s);
+  }
   a.B = P.B; a.C = P.C;
   a.pad_mode = P.mode; a.similarity = P.similarity; a.eps = P.eps;
   a.dbg = stream::g_debug_stamps;
@@ -33,14 +58,16 @@ int run(const KParams& P, int dtype, int mode, stream::StreamArgs a, cudaStream_
 
 bool stream_supported(const KParams& P, int dtype, int measure, int op) {
   if (!geometry_ok(P, measure)) return false;
+  if (split_ok(P, dtype, op_mode(op))) return true;
   return dtype == NFPB200_BF16 ? stream::plan_ok_bf16(P, op_mode(op)) : stream::plan_ok_f32(P, op_mode(op));
 }
 
 const char* stream_name(const KParams& P, int dtype, int measure, int op) {
-  (void)dtype; (void)measure; (void)op;
+  (void)measure;
+  const bool sp = split_ok(P, dtype, op_mode(op));
   const char* nm = "fused/stream";
 #define X(H_, W_, R_, TW_) \
-  if (P.H == H_ && P.W == W_ && P.R == R_) nm = "fused/stream_" #H_ "x" #W_ "_r" #R_;
+  if (P.H == H_ && P.W == W_ && P.R == R_) nm = sp ? "fused/split_" #H_ "x" #W_ "_r" #R_ : "fused/stream_" #H_ "x" #W_ "_r" #R_;
   NFP_STREAM_SHAPES(X)
 #undef X
   return nm;

@@ -49,159 +49,11 @@
 #define NFP_PASSB_FFMA2 1
 #endif
 
+#include "nfp_tables.cuh"
+
 namespace nfp {
 namespace stream {
 
-__host__ __device__ constexpr int align_up(int n, int a) { return (n + a - 1) / a * a; }
-
-template <int H_, int W_, int R_, int TW_>
-struct Cfg {
-  static constexpr int H = H_, W = W_, R = R_, TW = TW_;
-  static constexpr int k = 2 * R + 1, KK = k * k, K = KK - 1, CTR = R * k + R;
-  static constexpr int P = H * W;
-  static constexpr int NSX = W / TW;        // strips per row
-  static constexpr int NS = H * NSX;        // strips per channel plane
-  static constexpr int ND = K / 2;          // forward directions
-  static constexpr int NV = ND + 1;         // table entries per pixel: |x|^2 + ND dots
-  static constexpr int PNV = P * NV;
-  static constexpr int CPW = 32 / NS;       // channels per group (one warp pass)
-  static constexpr int LANES = CPW * NS;    // active lanes
-  static constexpr int XW = (NSX == 1) ? TW : TW + 2 * R;  // loaded columns per row (halo only if strips abut)
-  static constexpr int XOFF = (NSX == 1) ? 0 : R;          // column index of strip pixel 0 inside a loaded row
-  static constexpr int HALO = R * W + R;    // elements a strip may read before / after its channel plane
-  static constexpr bool PACK = (R == 1 && NSX == 1);  // pass A on packed fp32 pairs where the 96-register budget allows it
-  static constexpr int MINB = (R == 1) ? 2 : 1;  // CTAs per SM the register budget is sized for
-  // coefficient table Wd: one row of RS floats per map row (W pixels x KK offsets); padded to whole float4s where a
-  // lane strip is a full row, so the lane-per-channel pass B can fetch a row's coefficients with broadcast LDS.128
-  // (an ODD number of float4s per row: rows start 16-byte aligned and in different banks, so the strip form's
-  // per-lane coefficient loads stay conflict-free; other shapes keep the dense p*KK + o layout)
-  static constexpr bool LANECH = (NSX == 1 && P >= 49);  // shapes with a lane-per-channel pass B (measured: no gain on 2x2)
-  static constexpr int RS4 = align_up(W * KK, 4) / 4;
-  static constexpr int RS = LANECH ? 4 * (RS4 % 2 ? RS4 : RS4 + 1) : W * KK;
-  static constexpr int TASK = 64;                        // its work item: 64 channels = 2 per lane
-  __host__ __device__ static constexpr int widx(int p, int o) { return (p / W) * RS + (p % W) * KK + o; }
-  static_assert(W % TW == 0, "strip width must divide W");
-  static_assert(HALO * 4 <= 128, "the zeroed lead pad in front of the ring must cover the halo");
-  static_assert(NS <= 32 && CPW >= 1 && (CPW & (CPW - 1)) == 0, "channels per group must be a power of two");
-};
-
-// ---- compile-time stencil tables ----------------------------------------------------------------
-
-// taps that point outside the map (they fold back onto a window pixel under reflect / replicate padding)
-template <class C>
-constexpr int count_outside_taps() {
-  int n = 0;
-  for (int p = 0; p < C::P; ++p)
-    for (int o = 0; o < C::KK; ++o) {
-      if (o == C::CTR) continue;
-      const int qr = p / C::W + o / C::k - C::R, qc = p % C::W + o % C::k - C::R;
-      if (qr < 0 || qr >= C::H || qc < 0 || qc >= C::W) ++n;
-    }
-  return n;
-}
-
-template <class C>
-struct Tables {
-  // every array padded to a multiple of 16 bytes: the kernels fetch [fv, fd] (forward) or [q, fsrc, fdst, fptr]
-  // (backward) with one TMA bulk copy
-  static constexpr int NF = align_up(C::K * C::P, 8);
-  static constexpr int NQ = align_up(C::P * C::KK, 8);
-  static constexpr int NOUT = count_outside_taps<C>();
-  static constexpr int NFS = align_up(NOUT + 1, 8);
-  static constexpr int NFP = align_up(NOUT + 2, 8);
-  static constexpr int FWD_BYTES = 2 * NF * 2, BWD_BYTES = (NQ + 2 * NFS + NFP) * 2, BWD_OFFSET = FWD_BYTES;
-  alignas(16) int16_t fv[NF];   // forward: pixel the (padded) tap n of pixel p lands on, -1 = implicit zero
-  alignas(16) int16_t fd[NF];   // forward: index into the table of dot(p, fv)
-  alignas(16) int16_t q[NQ];    // window pixel p + off(o) when inside the map, else -1
-  // backward, folded taps in CSR form: window entry fdst[i] = p*KK + o of a border pixel p additionally receives
-  // the upstream gradient elements fsrc[fptr[i] .. fptr[i+1]) (flat n*P + p) of p's taps that point outside the
-  // map and are folded onto p + off(o) by the padding (o == CTR: onto p itself); fptr[NFP-1] = number of entries
-  alignas(16) int16_t fsrc[NFS];
-  alignas(16) int16_t fdst[NFS];
-  alignas(16) int16_t fptr[NFP];
-};
-
-constexpr int cmap_index(int i, int n, int mode) {
-  if (i >= 0 && i < n) return i;
-  if (mode == NFPB200_PAD_REFLECT) return i < 0 ? -i : 2 * (n - 1) - i;
-  if (mode == NFPB200_PAD_REPLICATE) return i < 0 ? 0 : n - 1;
-  return -1;
-}
-
-template <class C>
-constexpr Tables<C> make_tables(int mode) {
-  Tables<C> t{};
-  for (int p = 0; p < C::P; ++p)
-    for (int o = 0; o < C::KK; ++o) {
-      const int qr = p / C::W + o / C::k - C::R, qc = p % C::W + o % C::k - C::R;
-      t.q[p * C::KK + o] = (qr >= 0 && qr < C::H && qc >= 0 && qc < C::W) ? (int16_t)(qr * C::W + qc) : (int16_t)-1;
-    }
-  for (int n = 0; n < C::K; ++n) {
-    const int tt = n < (C::K >> 1) ? n : n + 1;  // row-major window with the centre removed (nfp.py:64-67)
-    const int ta = tt / C::k, tb = tt % C::k;
-    for (int p = 0; p < C::P; ++p) {
-      const int pr = p / C::W, pc = p % C::W;
-      const int vr = cmap_index(pr + ta - C::R, C::H, mode), vc = cmap_index(pc + tb - C::R, C::W, mode);
-      if (vr < 0 || vc < 0) {
-        t.fv[n * C::P + p] = -1;
-        t.fd[n * C::P + p] = 0;
-        continue;
-      }
-      const int v = vr * C::W + vc;
-      const int o = (vr - pr + C::R) * C::k + (vc - pc + C::R);
-      t.fv[n * C::P + p] = (int16_t)v;
-      t.fd[n * C::P + p] = (int16_t)(o == C::CTR ? p * C::NV
-                                                 : (o > C::CTR ? p * C::NV + (o - C::CTR) : v * C::NV + (C::CTR - o)));
-    }
-  }
-  // folded taps, grouped by the window entry they land on (border pixels only)
-  int nfd = 0, nfs = 0;
-  for (int p = 0; p < C::P; ++p) {
-    const int pr = p / C::W, pc = p % C::W;
-    if (pr >= C::R && pr < C::H - C::R && pc >= C::R && pc < C::W - C::R) continue;  // no tap leaves the map
-    int land[C::K] = {};  // window entry the outside tap n folds onto, -1 = none
-    for (int n = 0; n < C::K; ++n) {
-      const int tt = n < (C::K >> 1) ? n : n + 1;
-      const int rr = pr + tt / C::k - C::R, cc = pc + tt % C::k - C::R;
-      land[n] = -1;
-      if (rr >= 0 && rr < C::H && cc >= 0 && cc < C::W) continue;  // a direct tap
-      const int vr = cmap_index(rr, C::H, mode), vc = cmap_index(cc, C::W, mode);
-      if (vr < 0 || vc < 0) continue;  // zero padding
-      land[n] = (vr - pr + C::R) * C::k + (vc - pc + C::R);
-    }
-    for (int o = 0; o < C::KK; ++o) {
-      int cnt = 0;
-      for (int n = 0; n < C::K; ++n)
-        if (land[n] == o) {
-          if (cnt == 0) {
-            t.fdst[nfd] = (int16_t)(p * C::KK + o);
-            t.fptr[nfd] = (int16_t)nfs;
-          }
-          t.fsrc[nfs++] = (int16_t)(n * C::P + p);
-          ++cnt;
-        }
-      if (cnt) ++nfd;
-    }
-  }
-  t.fptr[nfd] = (int16_t)nfs;
-  t.fptr[Tables<C>::NFP - 1] = (int16_t)nfd;
-  return t;
-}
-
-template <class C, int PADMODE>
-__device__ const Tables<C> g_tables = make_tables<C>(PADMODE);
-
-template <class C>
-const Tables<C>* tables_for(int pad_mode) {
-  const Tables<C>* p = nullptr;
-  cudaError_t e;
-  switch (pad_mode) {
-    case NFPB200_PAD_REFLECT: e = cudaGetSymbolAddress((void**)&p, g_tables<C, NFPB200_PAD_REFLECT>); break;
-    case NFPB200_PAD_REPLICATE: e = cudaGetSymbolAddress((void**)&p, g_tables<C, NFPB200_PAD_REPLICATE>); break;
-    default: e = cudaGetSymbolAddress((void**)&p, g_tables<C, NFPB200_PAD_ZEROS>); break;
-  }
-  return e == cudaSuccess ? p : nullptr;
-}
 
 using namespace ptx;
 #define NFP_STAMP(k) do { if (a.dbg && tid == 0 && img == 0) a.dbg[(size_t)blockIdx.x * 8 + (k)] = globaltimer_ns(); } while (0)
@@ -254,7 +106,7 @@ struct Smem {
       gyraw = o;
     }
     uni = o;
-    wtab = take(NW * C::CPW * C::PNV * 4);
+    wtab = take(NW * C::PNV * 4);  // one partial table per warp (its channel slots are summed by shuffles first)
     const int u1 = o;
     o = uni;
     stg_warp = 2 * align_up(2 * C::CPW * C::P * ESZ, 16);
@@ -331,14 +183,26 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
       mbar_expect_tx(tabfull, TAB_BYTES);
       bulk_g2s(smem_raw + L.tabs, reinterpret_cast<const unsigned char*>(gt) + (BWD ? Tables<C>::BWD_OFFSET : 0),
                TAB_BYTES, tabfull);
-      grid_launch_dependents();  // PDL: the next grid may be scheduled as SM resources free up
       // PDL: the upstream gradient (and, without the x-stable hint, x) is produced by the preceding grid.  With the
       // hint the first image's x chunks go out first (a ring-full of them), the wait comes before its gradient loads.
+      // Dependents are released only AFTER this grid's own wait returned: an early-starting dependent then never
+      // overlaps the grid BEFORE this one, so the x-stable hint is safe in launch chains of any length.
       bool dep_pending = BWD && a.x_early;
-      if (!dep_pending) grid_dependency_wait();
+      if (!dep_pending) {
+        grid_dependency_wait();
+        grid_launch_dependents();
+      }
       int slot = 0, img = 0;
-      uint32_t ph = 0;
+      uint32_t phbits = 0;  // per-slot phase parity (the number of active stages may differ between the passes)
       const int npass = (BWD && !resident) ? 2 : 1;
+      // second CTA of an SM (blockIdx >= number of SMs): optionally starts later and streams pass A through fewer
+      // stages, so the SM's first CTA gets the larger share of the SM's load bandwidth and the two run out of phase
+      const bool second = (int)blockIdx.x >= a.nsm;
+      const int nactA = (second && !resident && a.y_stages > 0 && a.y_stages < nst) ? a.y_stages : nst;
+      if (second && a.y_delay_ns > 0) {
+        const unsigned long long t0 = globaltimer_ns();
+        while (globaltimer_ns() - t0 < (unsigned long long)a.y_delay_ns) {}
+      }
       auto load_grads = [&](int b, int img) {
         if (MODE == MODE_BWD) {
           const int par = img & 1;
@@ -360,20 +224,25 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
         int issued = 0;
         for (int pass = 0; pass < npass; ++pass) {
           const unsigned char* src = xb;
+          const int nact = pass == 0 ? nactA : nst;
+          slot = 0;
           for (int ch = 0; ch < NCH; ++ch, src += chunk_bytes, ++issued) {
-            if (dep_pending && issued == nst) {  // the ring is full of the first image's x: now wait, then its gradients
+            if (dep_pending && issued == nactA) {  // the ring is full of the first image's x: now wait, then its gradients
               grid_dependency_wait();
+              grid_launch_dependents();
               dep_pending = false;
               load_grads(b, img);
             }
-            mbar_wait(&empty[slot], ph ^ 1);
+            mbar_wait(&empty[slot], ((phbits >> slot) & 1u) ^ 1u);
             mbar_expect_tx(&full[slot], chunk_bytes);
             bulk_g2s(ring + slot * L.slot_stride, src, chunk_bytes, &full[slot]);
-            if (++slot == nst) { slot = 0; ph ^= 1; }
+            phbits ^= 1u << slot;
+            if (++slot == nact) slot = 0;
           }
         }
         if (dep_pending) {  // fewer chunks than ring stages
           grid_dependency_wait();
+          grid_launch_dependents();
           dep_pending = false;
           load_grads(b, img);
         }
@@ -412,11 +281,13 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
 #define NFP_OFF(dy, jj) (((dy) * W + (jj) - XOFF) * ESZ)
 
   int slot = 0, img = 0;
-  uint32_t ph = 0;
+  uint32_t phbits = 0;  // per-slot phase parity, in step with the producer's
+  const bool second = (int)blockIdx.x >= a.nsm;
+  const int nactA = (second && !resident && a.y_stages > 0 && a.y_stages < nst) ? a.y_stages : nst;
   NFP_STAMP(0);  // consumers ready
   for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++img) {
-    const int slot0 = slot;
-    const uint32_t ph0 = ph;
+    const uint32_t phbits0 = phbits;
+    slot = 0;
 
     // ---- backward, before pass A (overlaps the latency of the first chunk loads) or, with the x-stable hint,
     // right after it (pass A overlaps the tail of the preceding launch instead): the gy-only part of the
@@ -493,7 +364,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
 #pragma unroll
           for (int v = 0; v < NV; ++v) acc[j][v] = 0ull;
         for (int ch = 0; ch < NCH; ++ch) {
-          mbar_wait(&full[slot], ph);
+          mbar_wait(&full[slot], (phbits >> slot) & 1u);
           const unsigned char* sl = ring + slot * L.slot_stride;
           if constexpr (MODE == MODE_POOL_FWD) {
             // GAP(x) of this chunk's channels (NFP_Pooling.py:27): one lane per channel plane; the job rotates
@@ -540,7 +411,8 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);
           }
-          if (++slot == nst) { slot = 0; ph ^= 1; }
+          phbits ^= 1u << slot;
+          if (++slot == nactA) slot = 0;
         }
 #pragma unroll
         for (int j = 0; j < TW; ++j)
@@ -552,7 +424,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
 #pragma unroll
           for (int v = 0; v < NV; ++v) accs[j][v] = 0.f;
         for (int ch = 0; ch < NCH; ++ch) {
-          mbar_wait(&full[slot], ph);
+          mbar_wait(&full[slot], (phbits >> slot) & 1u);
           const unsigned char* sl = ring + slot * L.slot_stride;
           if constexpr (MODE == MODE_POOL_FWD) {
             // GAP(x) of this chunk's channels (NFP_Pooling.py:27): one lane per channel plane; the job rotates
@@ -602,12 +474,21 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);
           }
-          if (++slot == nst) { slot = 0; ph ^= 1; }
+          phbits ^= 1u << slot;
+          if (++slot == nactA) slot = 0;
         }
       }
-      // every active lane publishes its partial sums: table (warp, chslot), entries of strip `pos`
-      if (lane_on) {
-        float* wt = wtab + (warp * CPW + chslot) * PNV + pos * (TW * NV);
+      // sum over the channel slots of the warp (fixed shuffle tree: deterministic), then publish the warp's table
+      if constexpr (CPW > 1) {
+#pragma unroll
+        for (int d = LANES / 2; d >= NS; d >>= 1)
+#pragma unroll
+          for (int j = 0; j < TW; ++j)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) accs[j][v] += __shfl_down_sync(0xffffffffu, accs[j][v], d);
+      }
+      if (lane < NS) {
+        float* wt = wtab + warp * PNV + pos * (TW * NV);
 #pragma unroll
         for (int j = 0; j < TW; ++j)
 #pragma unroll
@@ -626,7 +507,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
     for (int i = tid; i < PNV; i += NT) {
       float s = 0.f;
 #pragma unroll 8
-      for (int t = 0; t < NW * CPW; ++t) s += wtab[t * PNV + i];  // fixed order: deterministic
+      for (int t = 0; t < NW; ++t) s += wtab[t * PNV + i];  // fixed order: deterministic
       tfull[i] = s;
       if (i % NV == 0) {  // |x_p|^2: the clamped inverse norm (and, backward, the 1/(N |x|) of the norm term)
         const int p = i / NV;
@@ -714,7 +595,8 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
         const int stg_half = L.stg_warp / 2;
         const float invP = 1.f / (float)P;
         unsigned char* gxb = reinterpret_cast<unsigned char*>(a.gx) + (size_t)b * a.C * P * ESZ;
-        if (resident) { slot = slot0; ph = ph0; }  // re-walk the slots pass A left in place
+        slot = 0;
+        if (resident) phbits = phbits0;  // re-walk the slots pass A left in place
         const float* ggx = nullptr;
         if constexpr (MODE == MODE_POOL_BWD) {
           if (a.ggx_tma) mbar_wait(&gyfull[img & 1], (img >> 1) & 1);  // bulk copy issued by the producer
@@ -732,7 +614,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
             const int ntask = CC / C::TASK;
             const float4* wd4 = reinterpret_cast<const float4*>(Wd);
             for (int ch = 0; ch < NCH; ++ch) {
-              mbar_wait(&full[slot], ph);
+              mbar_wait(&full[slot], (phbits >> slot) & 1u);
               unsigned char* sl = ring + slot * L.slot_stride;
               bool stored = false;
               for (int t = 0; t < ntask; ++t) {
@@ -799,7 +681,8 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
               if (stored && lane == 0) bulk_wait_read<0>();  // the slot goes back to the producer: the store has read it
               __syncwarp();
               if (lane == 0) mbar_arrive(&empty[slot]);
-              if (++slot == nst) { slot = 0; ph ^= 1; }
+              phbits ^= 1u << slot;
+              if (++slot == nst) slot = 0;
             }
             NFP_STAMP(3);  // pass B done (this warp)
           }
@@ -815,7 +698,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
             for (int o = 0; o < KK; ++o) wr[j][o] = wdp[j * KK + o];
         }
         for (int ch = 0; ch < NCH; ++ch) {
-          mbar_wait(&full[slot], ph);
+          mbar_wait(&full[slot], (phbits >> slot) & 1u);
           const unsigned char* sl = ring + slot * L.slot_stride;
           const unsigned char* pa = sl + warp * PSTRIDE + toff;
           for (int it = warp; it < npairs; it += NW, pa += NW * PSTRIDE) {
@@ -986,7 +869,8 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty[slot]);
-          if (++slot == nst) { slot = 0; ph ^= 1; }
+          phbits ^= 1u << slot;
+          if (++slot == nst) slot = 0;
         }
         NFP_STAMP(3);  // pass B done (this warp)
         if (lane == 0) bulk_wait_read<0>();  // staging is part of the union the next image overwrites
@@ -1074,6 +958,10 @@ int launch_mode(const KParams& P, StreamArgs a, cudaStream_t stream) {
   a.nst = pl.nst;
   a.resident = pl.resident;
   a.lanech = pl.lanech;
+  static const int y_delay = env_int("NFPB200_Y_DELAY_NS", 0);
+  static const int y_stages = env_int("NFPB200_Y_STAGES", 0);
+  a.y_delay_ns = y_delay;
+  a.y_stages = y_stages;
   auto kern = stream_kernel<T, C, MODE, kNW>;
   // per-device one-time setup (function attributes are per device; a process may drive several GPUs).
   // Idempotent, so a race between two host threads doing it at once is harmless.
@@ -1092,6 +980,7 @@ int launch_mode(const KParams& P, StreamArgs a, cudaStream_t stream) {
     sm_count[dev] = n;
   }
   const int num_sms = sm_count[dev];
+  a.nsm = num_sms;
   const Tables<C>* gt = tables_for<C>(a.pad_mode);
   if (!gt) return NFPB200_EINVAL;
   const int slots = num_sms * pl.ctas_per_sm;

@@ -158,7 +158,7 @@ def test_fused_cosine_vs_oracle(shape, mode, dtype, cuda_device):
         x = x.bfloat16().float()
     kw = dict(R=R, measure="cosine", padding=R, padding_mode=mode)
     cfg = NFPPooling(C, **kw).config
-    assert NF.describe(shape[:4], dtype, cfg).startswith("fused/stream"), "shape expected on the streaming fused path"
+    assert NF.describe(shape[:4], dtype, cfg).startswith(("fused/split", "fused/stream")), "shape expected on the streaming fused path"
     g = torch.randn(B, K, H, W, generator=gen)
     if dtype == torch.bfloat16:
         g = g.bfloat16().float()
@@ -196,7 +196,7 @@ def test_fused_stress_repeatable(shape, dtype, cuda_device):
         x, g = x.bfloat16().float(), g.bfloat16().float()
     kw = dict(R=R, measure="cosine", padding=R)
     cfg = NFPPooling(C, **kw).config
-    assert NF.describe(shape[:4], dtype, cfg).startswith("fused/stream")
+    assert NF.describe(shape[:4], dtype, cfg).startswith(("fused/split", "fused/stream"))
     sl = slice(B - 3, B)
     y_ref, gx_ref = O.nfp_forward_backward(x[sl].double(), g[sl].double(), **kw)
     tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
@@ -320,7 +320,7 @@ def test_pool_backward_gradient_row_alignment(shape, cuda_device):
     vals = torch.randn(B, C, generator=gen).to(cuda_device)
     buf = torch.empty(B * C + 4, device=cuda_device)
     desc = _capi.make_desc(_capi.F32, B, C, H, W, 1, 1, 1, 1, "reflect", "cosine", True, False, 1e-6, 1, 1e-6, "auto")
-    assert _capi.describe_path(desc, _capi.OP_POOL_BACKWARD).startswith("fused/stream")
+    assert _capi.describe_path(desc, _capi.OP_POOL_BACKWARD).startswith(("fused/split", "fused/stream"))
     lib = _capi.load()
     outs = []
     for off in (0, 1):   # 0: aligned rows, 1: the same values 4 bytes further (misaligned)

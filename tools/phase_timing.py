@@ -26,8 +26,12 @@ C, H, W, _ = SHAPES[args.shape]
 dev = torch.device("cuda:0")
 lb = LayerBench(dev, args.batch, C, H, W, args.R, args.dtype)
 lib = _capi.load()
-stamps = torch.zeros(8 * 1024, dtype=torch.int64, device=dev)
+stamps = torch.zeros(8 * 8 * 1024, dtype=torch.int64, device=dev)
 names = {"fwd": ["ready", "passA", "written"], "bwd": ["ready", "passA", "coef", "passB", "drained"]}
+# cluster-split kernels (one CTA per channel slice): extra stamps 5 = first sub-chunk landed, 6 = partial tables
+# exchanged, 7 = table reduced, 4 = CTA done; printed as per-CTA durations since the CTA's own start
+split_order = {"fwd": [(5, "landed"), (1, "passA"), (6, "xchg"), (7, "reduced"), (2, "written"), (4, "done")],
+               "bwd": [(5, "landed"), (1, "passA"), (6, "xchg"), (7, "reduced"), (2, "coef"), (3, "passB"), (4, "done")]}
 for which, fn in (("fwd", lb.fwd), ("bwd", lb.bwd)):
     for i in range(4):
         fn(i % lb.nbuf)
@@ -48,3 +52,13 @@ for which, fn in (("fwd", lb.fwd), ("bwd", lb.bwd)):
             col = (s[:, k] - t0) / 1e3
             line += f" {nm}: min {col.min():.1f} med {col.median():.1f} max {col.max():.1f} |"
         print(line)
+        if (s[:, 5] > 0).any():
+            line = f"   per-CTA (since its own start; start = {((s[:, 0] - t0) / 1e3).median():.1f} med / {((s[:, 0] - t0) / 1e3).max():.1f} max us after the first CTA) |"
+            for k, nm in split_order[which]:
+                col = (s[:, k] - s[:, 0]) / 1e3
+                col = col[s[:, k] > 0]
+                line += f" {nm}: {col.median():.2f} ({col.min():.2f}..{col.max():.2f}) |"
+            print(line)
+            starts = ((s[:, 0] - t0) / 1e3)
+            hist = torch.histc(starts.float(), bins=12, min=0, max=float(starts.max()) + 1e-3)
+            print("   CTA start histogram (12 bins up to %.1f us): %s" % (float(starts.max()), [int(v) for v in hist]))
