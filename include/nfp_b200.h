@@ -76,11 +76,19 @@ enum {
 };
 
 /* Optional hint, OR-ed into nfpb200_desc_t.path, for nfpb200_backward / nfpb200_pool_backward: `x` was NOT written by
- * the kernel that precedes this call on the stream (it is a saved forward activation, as under autograd).  The fused
- * backward kernels are launched with programmatic dependent launch; with the hint they start streaming x while the
- * preceding NFP kernel is still draining and only wait for it before touching the upstream gradient and gx.  Never
- * set it when x may be an output of the immediately preceding NFP launch (e.g. stacked NFP layers' forward). */
+ * the launch that immediately precedes this call on the stream (it is a saved forward activation, as under autograd).
+ * The fused backward kernels are launched with programmatic dependent launch; with the hint they start streaming x
+ * while the preceding kernel is still draining and only wait for it before touching the upstream gradient and gx.
+ * Every fused kernel releases its dependents only after its own dependency wait has returned, so the early reads can
+ * overlap nothing older than the immediately preceding launch: x may be the output of any EARLIER launch (stacked NFP
+ * layers, recomputation under activation checkpointing).  Do not set it when x is written by the immediately
+ * preceding launch itself. */
 #define NFPB200_HINT_X_STABLE 0x100
+
+/* Optional flag, OR-ed into nfpb200_desc_t.path, for nfpb200_forward with dtype = NFPB200_BF16: y is written as fp32
+ * (what the reference produces under torch.autocast on CUDA, where F.cosine_similarity runs in fp32 on the bf16
+ * neighbours, nfp.py:152-156).  Honoured by the fused kernels; other paths return NFPB200_EUNSUPPORTED. */
+#define NFPB200_FLAG_Y_F32 0x200
 
 /* operations, for nfpb200_workspace_bytes / nfpb200_describe_path */
 enum { NFPB200_OP_FORWARD = 0, NFPB200_OP_BACKWARD = 1, NFPB200_OP_POOL_FORWARD = 2, NFPB200_OP_POOL_BACKWARD = 3 };

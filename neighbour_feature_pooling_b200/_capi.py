@@ -27,6 +27,7 @@ MEASURES = {
 }
 PATHS = {"auto": 0, "generic": 1, "fused": 2}
 HINT_X_STABLE = 0x100   # NFPB200_HINT_X_STABLE, OR-ed into Desc.path for the backward entry points
+FLAG_Y_F32 = 0x200      # NFPB200_FLAG_Y_F32, OR-ed into Desc.path for nfpb200_forward with bf16 x: y is fp32
 OP_FORWARD, OP_BACKWARD, OP_POOL_FORWARD, OP_POOL_BACKWARD = 0, 1, 2, 3
 
 EXPORTS = (

@@ -12,6 +12,8 @@ using namespace nfp;
 
 namespace {
 
+constexpr int kPathFlags = NFPB200_HINT_X_STABLE | NFPB200_FLAG_Y_F32;
+
 int make_params(const nfpb200_desc_t* d, KParams* out) {
   if (!d || d->struct_bytes != (int32_t)sizeof(nfpb200_desc_t)) return NFPB200_EINVAL;
   if (d->dtype != NFPB200_F32 && d->dtype != NFPB200_BF16) return NFPB200_EINVAL;
@@ -19,8 +21,7 @@ int make_params(const nfpb200_desc_t* d, KParams* out) {
   if (d->R < 1 || d->stride < 1 || d->dilation < 1 || d->padding < 0) return NFPB200_EINVAL;
   if (d->padding_mode < NFPB200_PAD_ZEROS || d->padding_mode > NFPB200_PAD_CIRCULAR) return NFPB200_EINVAL;
   if (d->measure < 0 || d->measure >= NFPB200_NUM_MEASURES) return NFPB200_EINVAL;
-  if ((d->path & ~NFPB200_HINT_X_STABLE) < NFPB200_PATH_AUTO || (d->path & ~NFPB200_HINT_X_STABLE) > NFPB200_PATH_FUSED)
-    return NFPB200_EINVAL;
+  if ((d->path & ~kPathFlags) < NFPB200_PATH_AUTO || (d->path & ~kPathFlags) > NFPB200_PATH_FUSED) return NFPB200_EINVAL;
   KParams P{};
   P.B = d->B; P.C = d->C; P.H = d->H; P.W = d->W;
   P.R = d->R; P.k = 2 * d->R + 1; P.K = P.k * P.k - 1;
@@ -35,6 +36,7 @@ int make_params(const nfpb200_desc_t* d, KParams* out) {
   P.Wo = (P.W + 2 * P.pad - span) / P.stride + 1;
   P.similarity = d->similarity != 0;
   P.x_stable = (d->path & NFPB200_HINT_X_STABLE) != 0;
+  P.y_f32 = (d->path & NFPB200_FLAG_Y_F32) != 0 && d->dtype == NFPB200_BF16;
   P.diff_taps = d->difference_taps != 0;
   P.eps = d->eps; P.p = d->p; P.q = d->q_scs;
   P.pkind = P_GENERAL;
@@ -52,7 +54,7 @@ int make_params(const nfpb200_desc_t* d, KParams* out) {
 // 3 = planar, 2 = fused (cluster-split or streaming-ring kernels), 0 = generic, <0 = error
 int choose_path(const nfpb200_desc_t* d, const KParams& P, int op) {
   const int fused = stream_supported(P, d->dtype, d->measure, op) ? 2 : 0;
-  const int want = d->path & ~NFPB200_HINT_X_STABLE;
+  const int want = d->path & ~kPathFlags;
   if (want == NFPB200_PATH_FUSED) return fused ? fused : NFPB200_EUNSUPPORTED;
   if (want == NFPB200_PATH_GENERIC) return 0;
   if (fused) return fused;
@@ -168,6 +170,7 @@ int nfpb200_forward(const nfpb200_desc_t* desc, const void* x, void* y, void* wo
   if (!x || !y) return NFPB200_EINVAL;
   if (misaligned(x) || misaligned(y)) return NFPB200_EALIGN;
   NFP_PROLOGUE(NFPB200_OP_FORWARD)
+  if (P.y_f32 && path != 2) return NFPB200_EUNSUPPORTED;
   if (path == 3) return planar_forward(P, desc->dtype, x, y, ctx);
   if (path == 2) return stream_forward(P, desc->dtype, x, y, ctx);
   return generic_forward(P, desc->dtype, desc->measure, x, y, ctx);

@@ -20,6 +20,7 @@ struct KParams {
   int stride, pad, dil, mode;
   int Ho, Wo;
   int similarity, diff_taps, pkind;
+  int y_f32;            // NFPB200_FLAG_Y_F32: forward writes y as fp32 although x is bf16
   int x_stable;         // NFPB200_HINT_X_STABLE: x is not an output of the launch that precedes this one
   float eps, p, q;
 };

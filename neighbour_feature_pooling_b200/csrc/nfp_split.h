@@ -23,6 +23,7 @@ struct SplitArgs {
   int sub_ch;    // channels per sub-chunk (a whole number of work items)
   int pad_mode, similarity;
   int lanech;    // backward: lane-per-channel pass B (Cs a multiple of 64)
+  int y_f32;     // forward: y is fp32 regardless of T
   int x_early;   // backward: x is stable across the preceding launch -> load it before griddepcontrol.wait
   float eps;
   unsigned long long* dbg;  // optional: 8 globaltimer stamps per CTA, see nfpb200_debug_phase_timing

@@ -573,7 +573,8 @@ __global__ void __launch_bounds__(NW * 32, min_ctas<C>()) split_kernel(const Spl
         if constexpr (POOLED) {
           ytab[idx] = yv;
         } else {
-          reinterpret_cast<T*>(a.y)[((size_t)b * K + n) * P + p] = from_f32<T>(yv);
+          if (a.y_f32) reinterpret_cast<float*>(a.y)[((size_t)b * K + n) * P + p] = yv;
+          else reinterpret_cast<T*>(a.y)[((size_t)b * K + n) * P + p] = from_f32<T>(yv);
         }
       }
       if constexpr (POOLED) {

@@ -532,7 +532,8 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
         if constexpr (POOLED) {
           ytab[idx] = yv;
         } else {
-          reinterpret_cast<T*>(a.y)[(size_t)b * K * P + idx] = from_f32<T>(yv);
+          if (a.y_f32) reinterpret_cast<float*>(a.y)[(size_t)b * K * P + idx] = yv;
+          else reinterpret_cast<T*>(a.y)[(size_t)b * K * P + idx] = from_f32<T>(yv);
         }
       }
       if constexpr (POOLED) {

@@ -77,12 +77,16 @@ def shape_probe(x: torch.Tensor, cfg: NFPConfig) -> torch.Tensor:
     through the layer inside ``__init__`` under ``torch.no_grad()``
     (resnet18.py:22-25, nfp_heads.py:24-27, mobilenetv3.py:337-353).  This
     package has no CPU implementation, so a CPU input with autograd disabled is
-    answered with a NaN-filled tensor of the correct shape: ``.shape`` is all
-    those callers read, and any accidental use of the values is loud.
+    answered with a ZERO tensor of the correct shape.  Some of those callers pipe
+    the probe through train-mode ``BatchNorm`` layers (mobilenetv3.py:347-353),
+    which update their running statistics even under ``no_grad``: the values must
+    therefore be finite (a NaN probe would poison the running buffers for good).
+    The result carries no information beyond its shape; real CPU inference is
+    rejected whenever autograd is enabled, and documented as unsupported otherwise.
     """
     B, C, H, W = x.shape
     Ho, Wo = _check_geometry(H, W, cfg)
-    return torch.full((B, cfg.out_channels, Ho, Wo), float("nan"), dtype=x.dtype, device=x.device)
+    return torch.zeros((B, cfg.out_channels, Ho, Wo), dtype=x.dtype, device=x.device)
 
 
 def _reject_cpu(x: torch.Tensor):
@@ -97,16 +101,21 @@ _X_STABLE_HINT = os.environ.get("NFPB200_X_STABLE_HINT", "1") != "0"
 
 
 def _prepare(x: torch.Tensor):
-    """-> (tensor in a kernel dtype, dtype to return results in)"""
+    """-> (tensor in a kernel dtype, dtype to return results in)
+
+    Under ``torch.autocast('cuda')`` the reference extracts the neighbours with convs in the autocast dtype and then
+    runs ``F.cosine_similarity`` (``norm``, ``sum``, ``softmax`` ... for the other measures), which is on autocast's
+    fp32 list: its similarity map is float32.  A bf16 input therefore gives an fp32 map (the fused forward writes
+    fp32 directly, NFPB200_FLAG_Y_F32).  An fp32 input is NOT rounded to the autocast dtype first: the kernels
+    accumulate in fp32 anyway, so the result only differs from the reference's by the reference's own input rounding
+    (well inside the 2e-2 bf16 tolerance), and the cast kernel is saved."""
     if x.dim() != 4:
         raise RuntimeError(f"NFP expects a 4-D (B, C, H, W) input, got {tuple(x.shape)}")
     if not x.is_floating_point():
         raise RuntimeError(f"NFP expects a floating-point input, got {x.dtype}")
     out_dtype = x.dtype
-    if torch.is_autocast_enabled("cuda") and x.dtype == torch.float32:
-        # the reference's depthwise convs run in the autocast dtype (nfp.py:152-153)
-        out_dtype = torch.get_autocast_dtype("cuda")
-        x = x.to(out_dtype)
+    if torch.is_autocast_enabled("cuda"):
+        out_dtype = torch.float32
     if x.dtype == torch.float64:
         raise RuntimeError("NFP kernels compute in fp32; float64 inputs are not supported")
     if x.dtype not in _KERNEL_DTYPES:  # fp16: widen, the kernels accumulate in fp32 anyway
@@ -138,10 +147,17 @@ def _stream(device) -> int:
 
 class _NFPSimilarity(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, cfg):
+    def forward(ctx, x, cfg, y_f32=False):
         desc = _desc_for(x, cfg)
         Ho, Wo = _capi.output_shape(desc)
-        y = torch.empty((x.shape[0], cfg.out_channels, Ho, Wo), dtype=x.dtype, device=x.device)
+        # bf16 x, fp32 map (autocast): the fused kernels write fp32 directly; other paths write bf16 (widened by
+        # the caller)
+        y_f32 = bool(y_f32) and x.dtype == torch.bfloat16 and \
+            _capi.describe_path(desc, _capi.OP_FORWARD).startswith("fused/")
+        if y_f32:
+            desc.path |= _capi.FLAG_Y_F32
+        y = torch.empty((x.shape[0], cfg.out_channels, Ho, Wo), dtype=torch.float32 if y_f32 else x.dtype,
+                        device=x.device)
         with torch.cuda.device(x.device):
             ws, ws_ptr, ws_n = _workspace(desc, _capi.OP_FORWARD, x.device)
             rc = _capi.load().nfpb200_forward(ctypes.byref(desc), x.data_ptr(), y.data_ptr(), ws_ptr, ws_n,
@@ -171,7 +187,7 @@ class _NFPSimilarity(torch.autograd.Function):
             rc = _capi.load().nfpb200_backward(ctypes.byref(desc), x.data_ptr(), gy.data_ptr(), gx.data_ptr(),
                                                ws_ptr, ws_n, _stream(x.device))
         _capi.check(rc, "nfpb200_backward")
-        return gx, None
+        return gx, None, None
 
 
 class _NFPGapPair(torch.autograd.Function):
@@ -188,7 +204,7 @@ class _NFPGapPair(torch.autograd.Function):
         _capi.check(rc, "nfpb200_pool_forward")
         ctx.save_for_backward(x)
         ctx.cfg = cfg
-        return gap_x.to(x.dtype), gap_nfp.to(x.dtype)
+        return gap_x, gap_nfp
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -222,7 +238,7 @@ def nfp_similarity(x: torch.Tensor, cfg: NFPConfig) -> torch.Tensor:
     if x.dim() == 4:
         _check_geometry(x.shape[2], x.shape[3], cfg)
     xk, out_dtype = _prepare(x)
-    y = _NFPSimilarity.apply(xk, cfg)
+    y = _NFPSimilarity.apply(xk, cfg, out_dtype == torch.float32)
     return y if y.dtype == out_dtype else y.to(out_dtype)
 
 
@@ -233,10 +249,9 @@ def nfp_gap_pair(x: torch.Tensor, cfg: NFPConfig):
     if x.dim() == 4:
         _check_geometry(x.shape[2], x.shape[3], cfg)
     xk, out_dtype = _prepare(x)
-    gx, gn = _NFPGapPair.apply(xk, cfg)
-    if gx.dtype != out_dtype:
-        gx, gn = gx.to(out_dtype), gn.to(out_dtype)
-    return gx, gn
+    gx, gn = _NFPGapPair.apply(xk, cfg)   # both fp32 (the kernels accumulate in fp32)
+    # NFP_Pooling.py:27: avgpool(x) keeps the dtype of x (also under autocast); :31: the similarity map's dtype
+    return gx.to(x.dtype), gn.to(out_dtype)
 
 
 def describe(x_shape, dtype: torch.dtype, cfg: NFPConfig, op: int = _capi.OP_FORWARD) -> str:

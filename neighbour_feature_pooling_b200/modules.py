@@ -179,12 +179,23 @@ class nfp_pooling(nn.Module):
         self.nfp_proj = (nn.Linear(self.nfp_layer.out_channels, Params["num_ftrs"][Params["Model_name"]])
                          if Params else None)
 
+    def _fusable(self):
+        """The one-pass head (nfp_gap_pair) stands in for ``self.nfp_layer(x)`` only when that call would run the
+        stock operator: a subclass overriding ``forward``, a re-bound ``similarity_measure`` or forward hooks on the
+        layer must see the call, as in the reference (NFP_Pooling.py:29)."""
+        layer = self.nfp_layer
+        return (type(layer) in (NFPPooling, EnhancedNFPPooling)
+                and getattr(layer.similarity_measure, "__func__", None) is NFPPooling._measure
+                and getattr(layer.similarity_measure, "__self__", None) is layer
+                and not layer._forward_hooks and not layer._forward_pre_hooks
+                and not layer._backward_hooks and not layer._backward_pre_hooks)
+
     def forward(self, x):
         layer = self.nfp_layer
-        if isinstance(layer, NFPPooling) and x.device.type == "cuda":
+        if x.device.type == "cuda" and self._fusable():
             x_avg, x_nfp = NF.nfp_gap_pair(x, layer.config)
         else:
-            # foreign nfp_layer module, or a CPU shape probe (NFPPooling answers those itself)
+            # foreign / customised nfp_layer module, or a CPU shape probe (NFPPooling answers those itself)
             x_avg = self.avgpool(x).view(x.size(0), -1)
             x_nfp = layer(x)
             x_nfp = nn.functional.adaptive_avg_pool2d(x_nfp, (1, 1)).view(x_nfp.size(0), -1)

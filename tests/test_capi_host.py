@@ -95,8 +95,11 @@ def test_path_selection_and_workspace():
     hinted.path |= _capi.HINT_X_STABLE
     assert _capi.describe_path(hinted, _capi.OP_BACKWARD) == _capi.describe_path(fused, _capi.OP_BACKWARD)
     assert _capi.workspace_bytes(hinted, _capi.OP_BACKWARD) == 0
+    yf32 = _desc(B=256, C=512)
+    yf32.path |= _capi.FLAG_Y_F32          # fp32 similarity map from bf16 x (autocast): a flag like the hint
+    assert _capi.describe_path(yf32, _capi.OP_FORWARD) == _capi.describe_path(fused, _capi.OP_FORWARD)
     bad = _desc(B=256, C=512)
-    bad.path |= 0x200
+    bad.path |= 0x400
     assert _capi.load().nfpb200_workspace_bytes(ctypes.byref(bad), _capi.OP_BACKWARD, ctypes.byref(n)) == -1
     # every measure has a generic path
     for m in _capi.MEASURES:

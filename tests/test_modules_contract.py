@@ -65,7 +65,7 @@ def test_cpu_shape_probe_and_cpu_rejection():
     m = NFPPooling(8, R=1, measure="cosine", padding=1)
     with torch.no_grad():
         out = m(torch.randn(1, 8, 7, 7))
-    assert out.shape == (1, 8, 7, 7) and torch.isnan(out).all()
+    assert out.shape == (1, 8, 7, 7) and torch.isfinite(out).all()   # finite: probes may feed train-mode BatchNorm
     with torch.no_grad():
         assert NFPPooling(8, R=2, measure="cosine", padding=0, stride=2)(torch.randn(2, 8, 9, 11)).shape == (2, 24, 3, 4)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
@@ -74,6 +74,22 @@ def test_cpu_shape_probe_and_cpu_rejection():
         NFPPooling(8, measure="cosine", padding=2)(torch.randn(1, 8, 2, 2))
     with torch.no_grad(), pytest.raises(RuntimeError, match="Kernel size can't be greater"):
         NFPPooling(8, measure="cosine", padding=0)(torch.randn(1, 8, 2, 2))
+
+
+def test_shape_probe_keeps_batchnorm_buffers_finite():
+    """The reference's MOBILENETV3_NFP_INSERT.__init__ (mobilenetv3.py:337-353) pipes its CPU dummy through NFP and on
+    through train-mode Conv+BatchNorm blocks under no_grad: BatchNorm updates its running statistics there, so the
+    probe's values must be finite or every later eval() / checkpoint carries NaNs."""
+    import torch.nn as nn
+    nfp = NFPPooling(16, R=1, measure="cosine", padding=1)
+    tail = nn.Sequential(nn.Conv2d(nfp.out_channels, 16, 1, bias=False), nn.BatchNorm2d(16), nn.ReLU(),
+                         nn.Conv2d(16, 4, 3, padding=1), nn.BatchNorm2d(4))
+    tail.train()
+    with torch.no_grad():
+        out = tail(nfp(torch.randn(2, 16, 14, 14)))
+    assert out.shape == (2, 4, 14, 14)
+    for name, buf in tail.named_buffers():
+        assert torch.isfinite(buf).all(), name
 
 
 def test_wrapper_contract():

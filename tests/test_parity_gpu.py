@@ -387,11 +387,28 @@ def test_full_size_properties(C, H, W, R, dtype, cuda_device):
 
 
 def test_autocast_and_no_grad(cuda_device):
+    import torch.nn.functional as F
     layer = NFPPooling(64, R=1, measure="cosine", padding=1).to(cuda_device)
     x = torch.randn(2, 64, 7, 7, device=cuda_device)
+    xb = x.bfloat16()
+    y_ref = O.nfp_forward(xb.double().cpu(), R=1, measure="cosine", padding=1)
     with torch.autocast("cuda", dtype=torch.bfloat16):
+        # torch's own rule, which the reference inherits (nfp.py:156): cosine_similarity autocasts to fp32
+        assert F.cosine_similarity(xb, xb, dim=1).dtype == torch.float32
         y = layer(x)
-    assert y.dtype == torch.bfloat16          # the reference's convs run in the autocast dtype
+        yb = layer(xb)          # what a backbone under autocast hands over: bf16 in, fp32 similarity map out
+        xg = xb.clone().requires_grad_(True)
+        layer(xg).sum().backward()
+        head = nfp_pooling(layer).to(cuda_device)
+        h_avg, h_nfp = NF.nfp_gap_pair(x, layer.config)
+        hb_avg, hb_nfp = NF.nfp_gap_pair(xb, layer.config)
+    assert y.dtype == torch.float32 and yb.dtype == torch.float32
+    assert rel_err(yb.cpu(), y_ref) < 1e-5          # fp32 map of the bf16 input: no bf16 rounding of y
+    assert rel_err(y.cpu(), O.nfp_forward(x.double().cpu(), R=1, measure="cosine", padding=1)) < FP32_TOL
+    assert xg.grad.dtype == torch.bfloat16
+    # NFP_Pooling.py:27: avgpool(x) keeps x's dtype under autocast; :31 the pooled similarity is fp32
+    assert h_avg.dtype == torch.float32 and h_nfp.dtype == torch.float32
+    assert hb_avg.dtype == torch.bfloat16 and hb_nfp.dtype == torch.float32
     with torch.no_grad():
         y = layer(x)
     assert y.dtype == torch.float32 and not y.requires_grad
@@ -429,3 +446,122 @@ def test_resnet18_nfp_training_step_runs(cuda_device):
     assert out["images_per_s"] > 0 and np.isfinite(out["final_loss"])
     out32 = bench_train.run_gpu("ucmerced", batch=4, steps=2, warmup=1, amp=False)
     assert np.isfinite(out32["final_loss"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_x_stable_hint_in_stacked_chain(dtype, cuda_device):
+    """A.fwd -> B.fwd -> B.bwd(hint) with x_B = y_A (stacked NFP layers, or a recomputation that ends in an NFP
+    forward): the hinted backward may start streaming x_B early, but never before A.fwd -- the launch that wrote it --
+    has completed, because every fused kernel releases its dependents only after its own dependency wait.  Checked
+    against the conservative order (same bits) and the oracle, B = 256, 60 repeats, rotating buffers."""
+    import ctypes
+    from neighbour_feature_pooling_b200 import _capi
+    B, CA, H, W = 256, 512, 7, 7
+    CB = 8                                   # layer B consumes A's (B, 8, 7, 7) similarity map
+    kd = _capi.F32 if dtype == torch.float32 else _capi.BF16
+    gen = torch.Generator().manual_seed(23)
+    nbuf = 3
+    xa = [torch.randn(B, CA, H, W, generator=gen).to(cuda_device, dtype) for _ in range(nbuf)]
+    gyb = [torch.randn(B, 8, H, W, generator=gen).to(cuda_device, dtype) for _ in range(nbuf)]
+    dA = _capi.make_desc(kd, B, CA, H, W, 1, 1, 1, 1, "reflect", "cosine", True, False, 1e-6, 1, 1e-6, "auto")
+    dB = _capi.make_desc(kd, B, CB, H, W, 1, 1, 1, 1, "reflect", "cosine", True, False, 1e-6, 1, 1e-6, "auto")
+    assert _capi.describe_path(dA, _capi.OP_FORWARD).startswith("fused/")
+    assert _capi.describe_path(dB, _capi.OP_BACKWARD).startswith("fused/")
+    lib = _capi.load()
+    st = torch.cuda.current_stream().cuda_stream
+    res = {}
+    for hint in (0, _capi.HINT_X_STABLE):
+        dBb = _capi.make_desc(kd, B, CB, H, W, 1, 1, 1, 1, "reflect", "cosine", True, False, 1e-6, 1, 1e-6, "auto")
+        dBb.path |= hint
+        ya = [torch.zeros(B, 8, H, W, device=cuda_device, dtype=dtype) for _ in range(nbuf)]
+        yb = [torch.zeros(B, 8, H, W, device=cuda_device, dtype=dtype) for _ in range(nbuf)]
+        gxb = [torch.zeros(B, CB, H, W, device=cuda_device, dtype=dtype) for _ in range(nbuf)]
+        outs = []
+        for rep in range(60):
+            i = rep % nbuf
+            ya[i].fill_(float("nan"))       # a too-early read of x_B would see NaNs
+            _capi.check(lib.nfpb200_forward(ctypes.byref(dA), xa[i].data_ptr(), ya[i].data_ptr(), None, 0, st), "A.fwd")
+            _capi.check(lib.nfpb200_forward(ctypes.byref(dB), ya[i].data_ptr(), yb[i].data_ptr(), None, 0, st), "B.fwd")
+            _capi.check(lib.nfpb200_backward(ctypes.byref(dBb), ya[i].data_ptr(), gyb[i].data_ptr(), gxb[i].data_ptr(),
+                                             None, 0, st), "B.bwd")
+            if rep >= 60 - nbuf:
+                outs.append(gxb[i].clone())
+        torch.cuda.synchronize()
+        res[hint] = [t.float().cpu() for t in outs] + [t.float().cpu() for t in ya]
+    assert all(torch.isfinite(t).all() for t in res[_capi.HINT_X_STABLE])
+    assert all(torch.equal(a, b) for a, b in zip(res[0], res[_capi.HINT_X_STABLE]))
+    i = (60 - 1) % nbuf
+    y_a = res[0][nbuf + i][-2:]
+    _, gx_ref = O.nfp_forward_backward(y_a.double(), gyb[i][-2:].double().cpu(), R=1, measure="cosine", padding=1)
+    assert rel_err(res[_capi.HINT_X_STABLE][nbuf - 1][-2:], gx_ref) < (FP32_TOL if dtype == torch.float32 else BF16_TOL)
+
+
+POOL_CASES = [  # (B, C, H, W, R, mode, similarity)
+    (5, 64, 7, 7, 1, "zeros", True), (5, 64, 7, 7, 1, "replicate", True), (5, 64, 7, 7, 1, "reflect", False),
+    (3, 128, 7, 7, 2, "reflect", True), (3, 128, 7, 7, 2, "zeros", False), (2, 64, 14, 14, 1, "replicate", False),
+    (2, 64, 14, 14, 2, "reflect", True), (6, 512, 2, 2, 1, "reflect", True), (4, 32, 4, 4, 1, "zeros", False),
+    (2, 960, 7, 7, 1, "reflect", True), (3, 20, 9, 6, 1, "reflect", True), (2, 16, 28, 28, 1, "zeros", True),
+]
+
+
+@pytest.mark.parametrize("case", POOL_CASES, ids=lambda c: "x".join(map(str, c[:4])) + f"_r{c[4]}_{c[5]}_{'sim' if c[6] else 'dist'}")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_pooled_vs_oracle(case, dtype, cuda_device):
+    """nfpb200_pool_forward / nfpb200_pool_backward (the nfp_pooling head, NFP_Pooling.py:27-31) directly against the
+    oracle: GAP(x), GAP(NFP(x)) and the input gradient of <g1, GAP(x)> + <g2, GAP(NFP(x))>, for every padding mode,
+    similarity flag, window and dtype the fused kernels cover, plus shapes that fall to the other paths."""
+    B, C, H, W, R, mode, sim = case
+    K = (2 * R + 1) ** 2 - 1
+    gen = torch.Generator().manual_seed(B * 131 + C + 7 * H + R)
+    x = torch.randn(B, C, H, W, generator=gen)
+    x[0, :, 0, 0] = 0.0
+    g1 = torch.randn(B, C, generator=gen)
+    g2 = torch.randn(B, K, generator=gen)
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    kw = dict(R=R, measure="cosine", padding=R, padding_mode=mode, similarity=sim)
+    # oracle autograd: the upstream gradient of the map is g2 / (H*W), the same value over a tap plane
+    gy = (g2.double() / (H * W))[:, :, None, None].expand(B, K, H, W).contiguous()
+    y_map, gx_map = O.nfp_forward_backward(x.double(), gy, **kw)
+    y_map, gx_map = torch.as_tensor(np.asarray(y_map)), torch.as_tensor(np.asarray(gx_map))
+    gap_nfp_ref = y_map.mean((2, 3))
+    gx_ref = gx_map + (g1.double() / (H * W))[:, :, None, None]
+    gap_x_ref = x.double().mean((2, 3))
+    cfg = NFPPooling(C, **kw).config
+    xd = x.to(cuda_device, dtype).requires_grad_(True)
+    a, n = NF.nfp_gap_pair(xd, cfg)
+    ((a.float() * g1.to(cuda_device)).sum() + (n.float() * g2.to(cuda_device)).sum()).backward()
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert rel_err(a.detach().float().cpu(), gap_x_ref) < tol
+    assert rel_err(n.detach().float().cpu(), gap_nfp_ref) < tol
+    assert rel_err(xd.grad.float().cpu(), gx_ref) < tol
+
+
+def test_nfp_pooling_respects_customised_layers(cuda_device):
+    """The one-pass head replaces nfp_layer(x) only for the stock operator (NFP_Pooling.py:29 always calls the layer):
+    forward hooks, a re-bound similarity_measure and subclasses overriding forward must see the call."""
+    x = torch.randn(3, 64, 7, 7, device=cuda_device)
+    params = {"num_ftrs": {"m": 64}, "Model_name": "m", "Dataset": "d", "num_classes": {"d": 5}}
+    head = nfp_pooling(Params=params).to(cuda_device)
+    assert head._fusable()
+    base = head(x)
+    calls = []
+    h = head.nfp_layer.register_forward_hook(lambda m, i, o: calls.append(o.shape))
+    assert not head._fusable()
+    hooked = head(x)
+    h.remove()
+    assert calls == [(3, 8, 7, 7)] and rel_err(hooked.detach().cpu(), base.detach().cpu()) < 1e-6
+    head.nfp_layer.similarity_measure = lambda t: torch.ones(t.shape[0], 8, 7, 7, device=t.device)
+    assert not head._fusable()
+    ones = head(x)
+    want = x.mean((2, 3)) * head.nfp_proj(torch.ones(3, 8, device=cuda_device))
+    assert rel_err(ones.detach().cpu(), want.detach().cpu()) < 1e-6
+
+    class Doubled(NFPPooling):
+        def forward(self, t):
+            return 2 * super().forward(t)
+    head2 = nfp_pooling(nfp_layer=Doubled(64, R=1, measure="cosine", padding=1), Params=params).to(cuda_device)
+    head2.nfp_proj.load_state_dict(head.nfp_proj.state_dict())
+    assert not head2._fusable()
+    want2 = x.mean((2, 3)) * head.nfp_proj(2 * NFPPooling(64, R=1, measure="cosine", padding=1)(x).mean((2, 3)))
+    assert rel_err(head2(x).detach().cpu(), want2.detach().cpu()) < 1e-6
