@@ -14,8 +14,9 @@ of synthetic feature maps.  Default workload: BASELINE.json configs[1], ResNet18
                   HOST pinned buffers: H2D of x and grad_y and D2H of y and grad_x inside the timed region.
 * ``roofline`` -- the dominant kernel (backward): algorithmic bytes per launch / its average launch
                   duration (CUDA events around a graph of back-to-back launches on rotating buffers).
-* ``cpu_baseline`` -- the conv-form CPU port of the reference (oracle/nfp_convform.py) on the host cores.
-* ``--impl reference`` -- that CPU port as its own arm, same metric / config.
+* ``cpu_baseline`` -- the reference's own operator (staged unmodified under baseline/_ref by build()) on the host
+                  cores; the conv-form port (oracle/nfp_convform.py) only if those files are missing.
+* ``--impl reference`` -- that CPU path as its own arm, same metric / config.
 
 Multi-GPU (torchrun): the batch dimension is sharded, one process per GPU, no data-path collective;
 weak scaling (B maps per GPU per step); time = max over ranks.
@@ -59,6 +60,7 @@ def parse_args():
     ap.add_argument("--R", type=int, default=1)
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--windows", type=int, default=11, help="timed windows of --steps steps each; the median is reported")
     ap.add_argument("--no-sweep", action="store_true", help="skip the table over the other configs[1] cases")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the ResNet18+NFP training-step measurement")
@@ -206,9 +208,18 @@ class LayerBench:
                                        self.ws_n, s)
         self.capi.check(rc, "nfpb200_backward")
 
-    def step(self, i):
+    def cold(self, i):
+        """buffer set the backward of step i works on: not the one the step's forward has just read, so that x is
+        HBM-cold for the backward too (in a network the backward of a layer runs long after its forward)"""
+        return (i + self.nbuf // 2) % self.nbuf
+
+    def step(self, i):                # the headline step: conservative backward (no x-stable hint)
         self.fwd(i)
-        self.bwd(i)
+        self.bwd_conservative(self.cold(i))
+
+    def step_hinted(self, i):         # backward with NFPB200_HINT_X_STABLE, as the autograd function passes it
+        self.fwd(i)
+        self.bwd(self.cold(i))
 
     def bwd_conservative(self, i):   # without NFPB200_HINT_X_STABLE: the backward waits for the preceding launch first
         s = torch.cuda.current_stream(self.dev).cuda_stream
@@ -218,8 +229,7 @@ class LayerBench:
         self.capi.check(rc, "nfpb200_backward")
 
     def step_conservative(self, i):
-        self.fwd(i)
-        self.bwd_conservative(i)
+        self.step(i)
 
     # pooled mode (the nfp_pooling head, models/NFP_Pooling.py:25-36): GAP(x) and GAP(NFP(x)) from one pass over x,
     # backward from their two gradients; the similarity map is never written
@@ -252,7 +262,7 @@ class LayerBench:
 
     def pool_step(self, i):
         self.pool_fwd(i)
-        self.pool_bwd(i)
+        self.pool_bwd(self.cold(i))
 
     def _graph(self, fn, n, start):
         g = torch.cuda.CUDAGraph()
@@ -261,8 +271,11 @@ class LayerBench:
                 fn((start + j) % self.nbuf)
         return g
 
-    def timed(self, fn, steps, warmup, sampler=None, tag=None, barrier=None, chunk=250):
-        """Run `warmup` untimed then EXACTLY `steps` timed calls of fn (graph replays); returns seconds."""
+    def timed(self, fn, steps, warmup, sampler=None, tag=None, barrier=None, chunk=250, windows=1, reduce=None):
+        """Run `warmup` untimed calls, then `windows` timed windows of EXACTLY `steps` calls of fn each (graph
+        replays, CUDA events on the launching stream, barrier + synchronize on both sides of every window).
+        Returns the seconds of the MEDIAN window (after `reduce`, e.g. max over ranks, was applied to every window);
+        with windows > 1 also leaves the per-window list in self.last_windows."""
         for j in range(max(warmup, 3)):
             fn(j % self.nbuf)
         torch.cuda.synchronize(self.dev)
@@ -277,21 +290,26 @@ class LayerBench:
             done += n
         plan[0].replay()     # graph upload / first-replay cost stays outside the timed region
         torch.cuda.synchronize(self.dev)
-        if barrier:
-            barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if sampler:
-            sampler.tag = tag
-        torch.cuda.synchronize(self.dev)
-        e0.record()
-        for g in plan:
-            g.replay()
-        e1.record()
-        e1.synchronize()
-        if sampler:
-            sampler.tag = None
-        torch.cuda.synchronize(self.dev)
-        return e0.elapsed_time(e1) * 1e-3
+        times = []
+        for w in range(windows):
+            if barrier:
+                barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if sampler:
+                sampler.tag = tag
+            torch.cuda.synchronize(self.dev)
+            e0.record()
+            for g in plan:
+                g.replay()
+            e1.record()
+            e1.synchronize()
+            if sampler:
+                sampler.tag = None
+            torch.cuda.synchronize(self.dev)
+            t = e0.elapsed_time(e1) * 1e-3
+            times.append(reduce(t) if reduce else t)
+        self.last_windows = times
+        return sorted(times)[len(times) // 2]
 
 
 def e2e_through_module(dev, B, C, H, W, R, dtype_name, steps, warmup, sampler, barrier):
@@ -374,15 +392,46 @@ def e2e_through_module(dev, B, C, H, W, R, dtype_name, steps, warmup, sampler, b
 # ----------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the conv-form port of the reference on the host cores
 # ----------------------------------------------------------------------------------------------
-def cpu_port_setup(C, H, W, R, dtype_name, B):
-    from oracle.nfp_convform import ConvFormCosineNFP, forward_backward  # the only product-side use of oracle/
+def cpu_model_name():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    import platform
+    return platform.processor() or "unknown"
+
+
+def cpu_ref_setup(C, H, W, R, dtype_name, B):
+    """-> (callable running one fwd+bwd of the CPU arm on B maps, kind, description).
+
+    kind "reference": the UNMODIFIED reference operator (models/pooling/nfp.py, staged by __graft_entry__.build()
+    under the git-ignored baseline/_ref/ or read from /root/reference) -- NFPPooling(C, R, 'cosine', padding=R) forward
+    + autograd backward.  kind "port": the same ATen operator sequence restated (oracle/nfp_convform.py), used only
+    when the reference files are not there.  (bench.py's CPU legs are the only product-side use of oracle/.)"""
     tdtype = torch.float32 if dtype_name == "fp32" else torch.bfloat16
     K = (2 * R + 1) ** 2 - 1
-    layer = ConvFormCosineNFP(C, R=R, padding=R).to(tdtype)
     gen = torch.Generator().manual_seed(0)
     x = torch.randn(B, C, H, W, generator=gen).to(tdtype)
     g = torch.randn(B, K, H, W, generator=gen).to(tdtype)
-    return lambda: forward_backward(layer, x, g)
+    from oracle import ref_loader
+    if ref_loader.reference_available():
+        RefNFP, _ = ref_loader.load_reference()
+        layer = RefNFP(C, R=R, measure="cosine", padding=R).to(tdtype)
+
+        def run():
+            xr = x.detach().requires_grad_(True)
+            y = layer(xr)
+            y.backward(g)
+            return y, xr.grad
+        return run, "reference", ("the unmodified reference NFPPooling (models/pooling/nfp.py via baseline/_ref): "
+                                  "reflect-pad + one-hot depthwise convs + F.cosine_similarity + autograd")
+    from oracle.nfp_convform import ConvFormCosineNFP, forward_backward
+    layer = ConvFormCosineNFP(C, R=R, padding=R).to(tdtype)
+    return (lambda: forward_backward(layer, x, g)), "port", ("conv-form port of the reference's ATen chain "
+                                                             "(oracle/nfp_convform.py; reference files not staged)")
 
 
 def cpu_threads():
@@ -398,13 +447,13 @@ def cpu_threads():
 def cpu_baseline(C, H, W, R, dtype_name, B, budget_s):
     cores = cpu_threads()
     Bs = min(B, 32)
-    run = cpu_port_setup(C, H, W, R, dtype_name, Bs)
+    run, kind, what = cpu_ref_setup(C, H, W, R, dtype_name, Bs)
     run()
     t0 = time.perf_counter(); run(); dt = time.perf_counter() - t0
     rate = Bs / dt
     # size the timed sample to ~budget_s of wall time (x cores of CPU work), at most the full batch
     Bt = int(max(1, min(B, rate * budget_s / 3)))
-    run = cpu_port_setup(C, H, W, R, dtype_name, Bt)
+    run, kind, what = cpu_ref_setup(C, H, W, R, dtype_name, Bt)
     run()
     reps, t = 0, 0.0
     while reps < 3 or (t < budget_s and reps < 10):
@@ -412,25 +461,24 @@ def cpu_baseline(C, H, W, R, dtype_name, B, budget_s):
         reps += 1
         if t > 2 * budget_s:
             break
-    return {"value": reps * Bt / t, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{reps} x fwd+bwd of B={Bt} maps (same shape/dtype), conv-form port of the reference "
-                      f"(oracle/nfp_convform.py: reflect-pad + one-hot depthwise conv + F.cosine_similarity + autograd), "
+    return {"value": reps * Bt / t, "unit": UNIT, "cores": cores, "kind": kind, "cpu": cpu_model_name(),
+            "sample": f"{reps} x fwd+bwd of B={Bt} maps (same shape/dtype), {what}, "
                       f"torch {torch.__version__} CPU, {cores} threads, {t:.1f} s"}
 
 
 def run_reference_arm(args, C, H, W, where):
-    """--impl reference: the reference's CPU algorithm (conv-form port) as its own arm; rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = cpu_threads()
     B = args.batch
-    probe = cpu_port_setup(C, H, W, args.R, args.dtype, min(B, 16))
+    probe, kind, what = cpu_ref_setup(C, H, W, args.R, args.dtype, min(B, 16))
     probe()
     t0 = time.perf_counter(); probe(); rate = min(B, 16) / (time.perf_counter() - t0)
     total = args.steps + args.warmup
     Bs = int(max(1, min(B, rate * 150.0 / max(total, 1))))   # whole run within a few minutes
-    run = cpu_port_setup(C, H, W, args.R, args.dtype, Bs)
+    run, kind, what = cpu_ref_setup(C, H, W, args.R, args.dtype, Bs)
     for _ in range(args.warmup):
         run()
     t0 = time.perf_counter()
@@ -438,16 +486,18 @@ def run_reference_arm(args, C, H, W, where):
         run()
     dt = time.perf_counter() - t0
     value = args.steps * Bs / dt
-    sample = (f"each step = fwd+bwd of B={Bs} maps (bounded sample of the B={B} batch), conv-form port of the "
-              f"reference's ATen chain (oracle/nfp_convform.py), torch {torch.__version__} CPU, {cores} threads")
+    sample = (f"each step = fwd+bwd of B={Bs} maps (bounded sample of the B={B} batch), {what}, "
+              f"torch {torch.__version__} CPU, {cores} threads")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.dtype == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": workload_name(B, C, H, W, args.R, args.dtype), "source": where,
-                       "batch_per_step": Bs, "note": "the Python reference cannot travel to the GPU box; this is its "
-                                                     "operator sequence restated (kind=port), run on the host cores only"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                       "batch_per_step": Bs, "cpu": cpu_model_name(),
+                       "note": "the reference's CPU path on the host cores only (kind=reference: its own operator "
+                               "files, unmodified; kind=port: the same ATen sequence restated)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "cpu": cpu_model_name(),
+                             "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -525,19 +575,23 @@ def main():
     sampler.start()
 
     lb = LayerBench(dev, B, C, H, W, R, args.dtype)
-    # ---- value: K steps of fwd+bwd, device resident, HBM-cold via buffer rotation -------------------
-    t_step_total = lb.timed(lb.step, args.steps, args.warmup, sampler, "timed", barrier)
-    t_step_total = max_over_ranks(t_step_total)
+    # ---- value: K steps of fwd+bwd, device resident, HBM-cold via buffer rotation.  The K-step window is timed
+    # `--windows` times (each bracketed by barrier + synchronize, max over ranks) and the MEDIAN window is reported:
+    # at the driver's --steps 20 one window is 0.4 ms, where one late launch on one rank moves the number by 10 %.
+    t_step_total = lb.timed(lb.step, args.steps, args.warmup, sampler, "timed", barrier, windows=args.windows,
+                            reduce=max_over_ranks)
+    window_ms = [t * 1e3 for t in lb.last_windows]
     value = world * args.steps * B / t_step_total
     # ---- per-kernel launch durations (same rotation, back-to-back launches of one kernel) ---------
     sampler_tag = "kernels"
-    t_fwd = lb.timed(lb.fwd, args.steps, args.warmup, sampler, sampler_tag) / args.steps
-    t_bwd = lb.timed(lb.bwd, args.steps, args.warmup, sampler, sampler_tag) / args.steps
+    nk = max(args.steps, 100)
+    t_fwd = lb.timed(lb.fwd, nk, args.warmup, sampler, sampler_tag, windows=3) / nk
+    t_bwd = lb.timed(lb.bwd_conservative, nk, args.warmup, sampler, sampler_tag, windows=3) / nk
     fwd_bytes, bwd_bytes = algorithmic_bytes(B, C, H, W, R, lb.esz)
-    # the same without the x-stable hint (a backward that may not touch x before the preceding launch has finished)
-    n_cons = min(args.steps, 300)
-    t_step_cons = lb.timed(lb.step_conservative, n_cons, 5, sampler, "kernels") / n_cons
-    t_bwd_cons = lb.timed(lb.bwd_conservative, n_cons, 5, sampler, "kernels") / n_cons
+    # the same with the x-stable hint (the backward may stream x while the preceding launch drains)
+    n_cons = max(min(args.steps, 300), 100)
+    t_step_hint = lb.timed(lb.step_hinted, n_cons, 5, sampler, "kernels", windows=3) / n_cons
+    t_bwd_hint = lb.timed(lb.bwd, n_cons, 5, sampler, "kernels", windows=3) / n_cons
     # ---- e2e through the nn.Module API with host buffers ------------------------------------------------
     e2e_steps = min(args.steps, 50)
     t_e2e, h2d, d2h, _chk = e2e_through_module(dev, B, C, H, W, R, args.dtype, e2e_steps, min(args.warmup, 5),
@@ -606,14 +660,18 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_step_total / args.steps * 1e3, "higher_is_better": True,
+            "windows": {"n": len(window_ms), "steps_each": args.steps, "reported": "median window, max over ranks per window",
+                        "ms": [round(v, 5) for v in window_ms]},
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.dtype == "fp32" else "bf16",
             "data": "synthetic",
             "config": {"workload": workload_name(B, C, H, W, R, args.dtype), "source": where,
                        "batch_per_gpu": B, "global_batch": B * world, "sharding": f"batch over {world} GPU(s), no collective",
                        "l2_hygiene": f"inputs/outputs rotate over {lb.nbuf} buffer sets "
-                                     f"({lb.nbuf * lb.set_bytes / 2**20:.0f} MiB > 2x the 126 MiB L2), so every step is HBM-cold",
-                       "launch": "CUDA graph of C-ABI launches (nfpb200_forward + nfpb200_backward per step; the backward "
-                                 "with NFPB200_HINT_X_STABLE, as the autograd function passes it: x is a saved activation)",
+                                     f"({lb.nbuf * lb.set_bytes / 2**20:.0f} MiB > 2x the 126 MiB L2); a step's backward works "
+                                     f"on the set {lb.nbuf // 2} positions away from its forward's, so every kernel reads "
+                                     "HBM-cold inputs",
+                       "launch": "CUDA graph of C-ABI launches (nfpb200_forward + nfpb200_backward per step; conservative "
+                                 "backward: no NFPB200_HINT_X_STABLE -- see with_x_stable_hint for the hinted order)",
                        "kernel_path": {"forward": lb.path_fwd, "backward": lb.path_bwd}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": t_e2e / e2e_steps * 1e3,
@@ -631,13 +689,14 @@ def main():
                               "frac": (fwd_bytes + bwd_bytes) * args.steps / t_step_total / 1e9 / hbm_peak,
                               "bytes_per_step": fwd_bytes + bwd_bytes,
                               "bwd_share_of_step": t_bwd / (t_fwd + t_bwd)},
-            "without_x_stable_hint": {"us_per_step": t_step_cons * 1e6, "us_bwd": t_bwd_cons * 1e6,
-                                      "maps_per_s": world * B / t_step_cons,
-                                      "step_frac": (fwd_bytes + bwd_bytes) / t_step_cons / 1e9 / hbm_peak,
-                                      "bwd_frac": bwd_bytes / t_bwd_cons / 1e9 / hbm_peak,
-                                      "note": "NFPB200_HINT_X_STABLE (include/nfp_b200.h) lets a fused backward stream x "
-                                              "while the preceding NFP launch drains; it only matters when NFP launches "
-                                              "are adjacent on the stream, as in this microbenchmark"},
+            "with_x_stable_hint": {"us_per_step": t_step_hint * 1e6, "us_bwd": t_bwd_hint * 1e6,
+                                   "maps_per_s": world * B / t_step_hint,
+                                   "step_frac": (fwd_bytes + bwd_bytes) / t_step_hint / 1e9 / hbm_peak,
+                                   "bwd_frac": bwd_bytes / t_bwd_hint / 1e9 / hbm_peak,
+                                   "note": "NFPB200_HINT_X_STABLE (include/nfp_b200.h; what the autograd function passes: "
+                                           "x is a saved activation) lets a fused backward stream x while the preceding "
+                                           "launch drains; it only pays when NFP launches are adjacent on the stream, as "
+                                           "in this microbenchmark, so it is NOT the headline"},
             "clocks": sampler.summary(),
         }
         if cpu is not None:

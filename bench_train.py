@@ -70,18 +70,23 @@ def make_model(cfg, device, impl="b200"):
     if impl == "b200":
         import neighbour_feature_pooling_b200 as nfpb
         pool = nfpb.nfp_pooling(Params=Params)
-    else:  # CPU baseline: the conv-form port of the reference operator inside the reference's wrapper maths
-        from oracle.nfp_convform import ConvFormCosineNFP
+    else:  # CPU baseline: the reference's own nfp_pooling (staged under baseline/_ref), else its conv-form port
+        from oracle import ref_loader
+        if ref_loader.reference_available():
+            _, ref_pool = ref_loader.load_reference()
+            pool = ref_pool(Params=Params)
+        else:
+            from oracle.nfp_convform import ConvFormCosineNFP
 
-        class RefPool(nn.Module):
-            def __init__(self):
-                super().__init__()
-                self.nfp_layer = ConvFormCosineNFP(512, R=1, padding=1)
-                self.nfp_proj = nn.Linear(8, 512)
+            class RefPool(nn.Module):
+                def __init__(self):
+                    super().__init__()
+                    self.nfp_layer = ConvFormCosineNFP(512, R=1, padding=1)
+                    self.nfp_proj = nn.Linear(8, 512)
 
-            def forward(self, x):
-                return x.mean((2, 3)) * self.nfp_proj(self.nfp_layer(x).mean((2, 3)))
-        pool = RefPool()
+                def forward(self, x):
+                    return x.mean((2, 3)) * self.nfp_proj(self.nfp_layer(x).mean((2, 3)))
+            pool = RefPool()
     return ResNet18_NFPPooling(cfg["classes"], cfg["in_chans"], pool).to(device)
 
 
@@ -235,7 +240,9 @@ def run_cpu_baseline(config="eurosat", batch=8, steps=2):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return {"images_per_s": steps * batch / dt, "cores": torch.get_num_threads(), "kind": "port",
+    from oracle import ref_loader
+    return {"images_per_s": steps * batch / dt, "cores": torch.get_num_threads(),
+            "kind": "reference" if ref_loader.reference_available() else "port",
             "sample": f"{steps} x fwd+bwd+Adam of batch {batch}, fp32, torch {torch.__version__} CPU"}
 
 

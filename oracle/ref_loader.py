@@ -12,11 +12,33 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("NFP_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the reference checkout (build container), else the copy of its two operator files that __graft_entry__.build()
+# leaves under the git-ignored baseline/_ref/ (it travels to the GPU box with the repo snapshot)
+STAGED_ROOT = os.path.join(_REPO, "baseline", "_ref")
+REFERENCE_ROOT = os.environ.get("NFP_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isfile("/root/reference/models/pooling/nfp.py") else STAGED_ROOT)
+OPERATOR_FILES = ("models/__init__.py", "models/pooling/nfp.py", "models/NFP_Pooling.py")
 
 
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "pooling", "nfp.py"))
+
+
+def stage_reference(src_root: str = "/root/reference") -> bool:
+    """Copy the reference's two operator files (unmodified) to baseline/_ref/ so that bench.py can time the REAL
+    reference on a box that has no /root/reference.  baseline/_ref/ is git-ignored: nothing enters the history."""
+    import shutil
+    if not os.path.isfile(os.path.join(src_root, "models", "pooling", "nfp.py")):
+        return os.path.isfile(os.path.join(STAGED_ROOT, "models", "pooling", "nfp.py"))
+    for rel in OPERATOR_FILES:
+        src, dst = os.path.join(src_root, rel), os.path.join(STAGED_ROOT, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if os.path.isfile(src):
+            shutil.copyfile(src, dst)
+        elif rel.endswith("__init__.py"):
+            open(dst, "w").close()
+    return True
 
 
 def load_reference():

@@ -76,4 +76,4 @@ def test_train_harness_cpu_reference_arm():
     out = model(torch.randn(2, cfg["in_chans"], cfg["size"], cfg["size"]))
     assert out.shape == (2, cfg["classes"])
     r = bench_train.run_cpu_baseline("eurosat", batch=2, steps=1)
-    assert r["images_per_s"] > 0 and r["kind"] == "port"
+    assert r["images_per_s"] > 0 and r["kind"] in ("reference", "port")
