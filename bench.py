@@ -162,7 +162,7 @@ class ClockSampler:
 class LayerBench:
     """Rotating device buffers + C-ABI launches for one (shape, R, dtype) configuration."""
 
-    def __init__(self, dev, B, C, H, W, R, dtype_name, seed=0):
+    def __init__(self, dev, B, C, H, W, R, dtype_name, seed=0, layout="nchw"):
         from neighbour_feature_pooling_b200 import _capi
         self.capi = _capi
         self.lib = _capi.load()
@@ -171,11 +171,13 @@ class LayerBench:
         self.K = (2 * R + 1) ** 2 - 1
         self.tdtype = torch.float32 if dtype_name == "fp32" else torch.bfloat16
         self.esz = 4 if dtype_name == "fp32" else 2
+        lay = _capi.LAYOUT_NHWC if layout == "nhwc" else _capi.LAYOUT_NCHW   # nhwc: channels_last x / grad_x, in place
+        self.layout = layout
         self.desc = _capi.make_desc(_capi.F32 if dtype_name == "fp32" else _capi.BF16, B, C, H, W, R, 1, R, 1,
-                                    "reflect", "cosine", True, False, 1e-6, 1, 1e-6, "auto")
+                                    "reflect", "cosine", True, False, 1e-6, 1, 1e-6, "auto", layout=lay)
         # backward entry points: x is a saved activation, not an output of the preceding launch (what autograd passes)
         self.desc_bwd = _capi.make_desc(_capi.F32 if dtype_name == "fp32" else _capi.BF16, B, C, H, W, R, 1, R, 1,
-                                        "reflect", "cosine", True, False, 1e-6, 1, 1e-6, "auto")
+                                        "reflect", "cosine", True, False, 1e-6, 1, 1e-6, "auto", layout=lay)
         if os.environ.get("NFPB200_BENCH_NO_HINT", "0") != "1":
             self.desc_bwd.path |= _capi.HINT_X_STABLE
         self.path_fwd = _capi.describe_path(self.desc, _capi.OP_FORWARD)
@@ -186,10 +188,12 @@ class LayerBench:
         self.nbuf = max(4, math.ceil(2.2 * L2_BYTES / set_bytes))
         gen = torch.Generator(device=dev).manual_seed(seed)
         mk = lambda *s: torch.randn(*s, device=dev, generator=gen).to(self.tdtype)
-        self.x = [mk(B, C, H, W) for _ in range(self.nbuf)]
+        fmt = torch.channels_last if layout == "nhwc" else torch.contiguous_format
+        self.x = [mk(B, C, H, W).contiguous(memory_format=fmt) for _ in range(self.nbuf)]
         self.gy = [mk(B, self.K, H, W) for _ in range(self.nbuf)]
         self.y = [torch.empty(B, self.K, H, W, device=dev, dtype=self.tdtype) for _ in range(self.nbuf)]
-        self.gx = [torch.empty(B, C, H, W, device=dev, dtype=self.tdtype) for _ in range(self.nbuf)]
+        self.gx = [torch.empty(B, C, H, W, device=dev, dtype=self.tdtype).contiguous(memory_format=fmt)
+                   for _ in range(self.nbuf)]
         wsf = _capi.workspace_bytes(self.desc, _capi.OP_FORWARD)
         wsb = _capi.workspace_bytes(self.desc, _capi.OP_BACKWARD)
         self.ws = torch.empty(max(wsf, wsb, 1), dtype=torch.uint8, device=dev)
@@ -616,19 +620,23 @@ def main():
     # ---- the other configs[1] cases (reported, not part of `value`) -------------------------------------
     sweep = []
     if not args.no_sweep and rank == 0:
-        cases = [(shp, r, dt) for shp in ("l4", "l3") for r in (1, 2) for dt in ("fp32", "bf16")]
-        cases += [("mbv3", 1, "fp32"), ("vit", 1, "bf16"), ("eurosat", 1, "fp32")]   # configs[3], [4], [2] head maps
-        for shp, r, dt in cases:
+        cases = [(shp, r, dt, "nchw") for shp in ("l4", "l3") for r in (1, 2) for dt in ("fp32", "bf16")]
+        cases += [("mbv3", 1, "fp32", "nchw"), ("vit", 1, "bf16", "nchw"), ("eurosat", 1, "fp32", "nchw")]   # configs[3], [4], [2]
+        # channels-last / token layout consumed in place by the tensor-core kernels
+        cases += [("vit", 1, "bf16", "nhwc"), ("l4", 1, "bf16", "nhwc"), ("l4", 2, "bf16", "nhwc"), ("l3", 1, "bf16", "nhwc"),
+                  ("mbv3", 1, "bf16", "nhwc")]
+        for shp, r, dt, lay in cases:
             if True:
                 if True:
                     c, h, w, _ = SHAPES[shp]
-                    s = LayerBench(dev, B, c, h, w, r, dt)
-                    n = min(args.steps, 200)
+                    s = LayerBench(dev, B, c, h, w, r, dt, layout=lay)
+                    n = max(min(args.steps, 200), 60)
                     tt = s.timed(s.step, n, 5, sampler, "sweep") / n
                     tf = s.timed(s.fwd, n, 5, sampler, "sweep") / n
                     tb = s.timed(s.bwd, n, 5, sampler, "sweep") / n
                     fb, bb = algorithmic_bytes(B, c, h, w, r, s.esz)
-                    sweep.append({"workload": workload_name(B, c, h, w, r, dt), "maps_per_s": B / tt,
+                    sweep.append({"workload": workload_name(B, c, h, w, r, dt) + (" channels-last" if lay == "nhwc" else ""),
+                                  "maps_per_s": B / tt,
                                   "us_per_step": tt * 1e6, "us_fwd": tf * 1e6, "us_bwd": tb * 1e6,
                                   "step_gbs": (fb + bb) / tt / 1e9, "step_frac": (fb + bb) / tt / 1e9 / hbm_peak,
                                   "bwd_frac": bb / tb / 1e9 / hbm_peak, "fwd_frac": fb / tf / 1e9 / hbm_peak,

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define NFPB200_ABI_VERSION 1
+#define NFPB200_ABI_VERSION 2
 
 /* element type of x / y / gy / gx.  Accumulation is always fp32. */
 enum { NFPB200_F32 = 0, NFPB200_BF16 = 1 };
@@ -66,6 +66,16 @@ enum {
   NFPB200_SMITH = 15,      /* nfp.py:326-342 */
   NFPB200_SCS = 16,        /* nfp.py:344-374 ('scs' / 'sharpened_cosine'), batch-coupled as in the reference */
   NFPB200_NUM_MEASURES = 17
+};
+
+/* memory layout of x and gx.  y / gy are always (B, K, H', W') contiguous, the layout the reference returns. */
+enum {
+  NFPB200_LAYOUT_NCHW = 0,  /* (B, C, H, W) contiguous */
+  NFPB200_LAYOUT_NHWC = 1   /* x[b][h][w][c]: channels of a pixel contiguous, pixels dense, batch stride free.  This is a
+                               torch channels_last map and the ViT head's token view (models/texture_pooling.py:181-188:
+                               feats[:, 1:].transpose(1, 2).reshape(B, C, H, W), strides (197*C, 1, W*C, C)); served by
+                               the tensor-core "fused/token" kernels (bf16, cosine, pad = R, stride 1) -- anything else
+                               returns NFPB200_EUNSUPPORTED and the caller repacks to NCHW */
 };
 
 /* which implementation to use */
@@ -121,7 +131,11 @@ typedef struct nfpb200_desc {
   float eps;                /* nfp.py:33 */
   float p;                  /* nfp.py:30: ord of NORM (INFINITY allowed), exponent of SCS */
   float q_scs;              /* nfp.py:34 */
-  int32_t path;             /* NFPB200_PATH_* [| NFPB200_HINT_X_STABLE] */
+  int32_t path;             /* NFPB200_PATH_* [| NFPB200_HINT_X_STABLE] [| NFPB200_FLAG_Y_F32] */
+  int32_t layout;           /* NFPB200_LAYOUT_*; 0 = NCHW */
+  int32_t reserved0;        /* must be 0 */
+  int64_t x_batch_stride;   /* NHWC only: elements between consecutive images of x; 0 = dense (H*W*C); multiple of 8 */
+  int64_t gx_batch_stride;  /* NHWC only: the same for gx */
 } nfpb200_desc_t;
 
 int nfpb200_abi_version(void);

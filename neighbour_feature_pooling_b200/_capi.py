@@ -15,7 +15,7 @@ import threading
 _LIB_PATH = os.environ.get("NFPB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
                                                           "libnfp_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 F32, BF16 = 0, 1
 PAD_MODES = {"zeros": 0, "reflect": 1, "replicate": 2, "circular": 3}
@@ -29,6 +29,7 @@ PATHS = {"auto": 0, "generic": 1, "fused": 2}
 HINT_X_STABLE = 0x100   # NFPB200_HINT_X_STABLE, OR-ed into Desc.path for the backward entry points
 FLAG_Y_F32 = 0x200      # NFPB200_FLAG_Y_F32, OR-ed into Desc.path for nfpb200_forward with bf16 x: y is fp32
 OP_FORWARD, OP_BACKWARD, OP_POOL_FORWARD, OP_POOL_BACKWARD = 0, 1, 2, 3
+LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 
 EXPORTS = (
     "nfpb200_abi_version", "nfpb200_status_string", "nfpb200_output_shape",
@@ -48,6 +49,8 @@ class Desc(ctypes.Structure):
         ("similarity", ctypes.c_int32), ("difference_taps", ctypes.c_int32),
         ("eps", ctypes.c_float), ("p", ctypes.c_float), ("q_scs", ctypes.c_float),
         ("path", ctypes.c_int32),
+        ("layout", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("x_batch_stride", ctypes.c_int64), ("gx_batch_stride", ctypes.c_int64),
     ]
 
 
@@ -114,7 +117,8 @@ def check(rc: int, what: str):
 
 def make_desc(dtype: int, B: int, C: int, H: int, W: int, R: int, stride: int, padding: int,
               dilation: int, padding_mode: str, measure: str, similarity: bool,
-              difference_taps: bool, eps: float, p: float, q_scs: float, path: str = "auto") -> Desc:
+              difference_taps: bool, eps: float, p: float, q_scs: float, path: str = "auto",
+              layout: int = 0, x_batch_stride: int = 0, gx_batch_stride: int = 0) -> Desc:
     d = Desc()
     d.struct_bytes = ctypes.sizeof(Desc)
     d.dtype = dtype
@@ -128,6 +132,10 @@ def make_desc(dtype: int, B: int, C: int, H: int, W: int, R: int, stride: int, p
     d.p = float(p) if not (isinstance(p, str)) else (math.inf if p == "inf" else float(p))
     d.q_scs = float(q_scs)
     d.path = PATHS[path]
+    d.layout = layout
+    d.reserved0 = 0
+    d.x_batch_stride = x_batch_stride
+    d.gx_batch_stride = gx_batch_stride
     return d
 
 

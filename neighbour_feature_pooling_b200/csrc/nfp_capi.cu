@@ -34,6 +34,16 @@ int make_params(const nfpb200_desc_t* d, KParams* out) {
   if (P.H + 2 * P.pad < span || P.W + 2 * P.pad < span) return NFPB200_ESHAPE;
   P.Ho = (P.H + 2 * P.pad - span) / P.stride + 1;
   P.Wo = (P.W + 2 * P.pad - span) / P.stride + 1;
+  if (d->layout != NFPB200_LAYOUT_NCHW && d->layout != NFPB200_LAYOUT_NHWC) return NFPB200_EINVAL;
+  if (d->reserved0 != 0 || d->x_batch_stride < 0 || d->gx_batch_stride < 0) return NFPB200_EINVAL;
+  P.layout = d->layout;
+  P.x_batch_stride = d->x_batch_stride;
+  P.gx_batch_stride = d->gx_batch_stride;
+  if (P.layout == NFPB200_LAYOUT_NHWC) {
+    const long long dense = (long long)P.H * P.W * P.C;
+    if ((P.x_batch_stride && P.x_batch_stride < dense) || (P.gx_batch_stride && P.gx_batch_stride < dense)) return NFPB200_EINVAL;
+    if (P.x_batch_stride % 8 || P.gx_batch_stride % 8) return NFPB200_EALIGN;
+  }
   P.similarity = d->similarity != 0;
   P.x_stable = (d->path & NFPB200_HINT_X_STABLE) != 0;
   P.y_f32 = (d->path & NFPB200_FLAG_Y_F32) != 0 && d->dtype == NFPB200_BF16;
@@ -51,8 +61,12 @@ int make_params(const nfpb200_desc_t* d, KParams* out) {
   return NFPB200_OK;
 }
 
-// 3 = planar, 2 = fused (cluster-split or streaming-ring kernels), 0 = generic, <0 = error
+// 4 = token (channels-last), 3 = planar, 2 = fused (cluster-split or streaming-ring kernels), 0 = generic, <0 = error
 int choose_path(const nfpb200_desc_t* d, const KParams& P, int op) {
+  if (P.layout == NFPB200_LAYOUT_NHWC) {
+    if ((d->path & ~kPathFlags) == NFPB200_PATH_GENERIC) return NFPB200_EUNSUPPORTED;
+    return token_supported(P, d->dtype, d->measure, op) ? 4 : NFPB200_EUNSUPPORTED;
+  }
   const int fused = stream_supported(P, d->dtype, d->measure, op) ? 2 : 0;
   const int want = d->path & ~kPathFlags;
   if (want == NFPB200_PATH_FUSED) return fused ? fused : NFPB200_EUNSUPPORTED;
@@ -64,6 +78,7 @@ int choose_path(const nfpb200_desc_t* d, const KParams& P, int op) {
 
 size_t path_workspace_bytes(int path, const nfpb200_desc_t* d, const KParams& P, int op) {
   if (path == 3) return planar_workspace_bytes(P, op);
+  if (path == 4) return 0;
   return path ? 0 : generic_workspace_bytes(P, d->dtype, d->measure, op);
 }
 
@@ -135,7 +150,7 @@ int nfpb200_describe_path(const nfpb200_desc_t* desc, int32_t op, char* buf, siz
   int path = choose_path(desc, P, op);
   if (path < 0) return path;
   snprintf(buf, buf_bytes, "%s",
-           path == 3 ? planar_name(P, desc->dtype, op)
+           path == 4 ? token_name(P) : path == 3 ? planar_name(P, desc->dtype, op)
                      : (path == 2 ? stream_name(P, desc->dtype, desc->measure, op) : "generic/pairs"));
   return NFPB200_OK;
 }
@@ -147,7 +162,7 @@ int nfpb200_launch_count(const nfpb200_desc_t* desc, int32_t op, int32_t* launch
   if (!launches || op < NFPB200_OP_FORWARD || op > NFPB200_OP_POOL_BACKWARD) return NFPB200_EINVAL;
   int path = choose_path(desc, P, op);
   if (path < 0) return path;
-  *launches = path == 3 ? planar_launch_count(op) : (path ? 1 : generic_launch_count(P, desc->dtype, desc->measure, op));
+  *launches = path == 4 ? 1 : path == 3 ? planar_launch_count(op) : (path ? 1 : generic_launch_count(P, desc->dtype, desc->measure, op));
   return NFPB200_OK;
 }
 
@@ -170,7 +185,8 @@ int nfpb200_forward(const nfpb200_desc_t* desc, const void* x, void* y, void* wo
   if (!x || !y) return NFPB200_EINVAL;
   if (misaligned(x) || misaligned(y)) return NFPB200_EALIGN;
   NFP_PROLOGUE(NFPB200_OP_FORWARD)
-  if (P.y_f32 && path != 2) return NFPB200_EUNSUPPORTED;
+  if (P.y_f32 && path != 2 && path != 4) return NFPB200_EUNSUPPORTED;
+  if (path == 4) return token_run(P, NFPB200_OP_FORWARD, x, nullptr, y, nullptr, nullptr, nullptr, nullptr, nullptr, ctx);
   if (path == 3) return planar_forward(P, desc->dtype, x, y, ctx);
   if (path == 2) return stream_forward(P, desc->dtype, x, y, ctx);
   return generic_forward(P, desc->dtype, desc->measure, x, y, ctx);
@@ -181,6 +197,7 @@ int nfpb200_backward(const nfpb200_desc_t* desc, const void* x, const void* gy, 
   if (!x || !gy || !gx) return NFPB200_EINVAL;
   if (misaligned(x) || misaligned(gy) || misaligned(gx)) return NFPB200_EALIGN;
   NFP_PROLOGUE(NFPB200_OP_BACKWARD)
+  if (path == 4) return token_run(P, NFPB200_OP_BACKWARD, x, gy, nullptr, gx, nullptr, nullptr, nullptr, nullptr, ctx);
   if (path == 3) return planar_backward(P, desc->dtype, x, gy, gx, ctx);
   if (path == 2) return stream_backward(P, desc->dtype, x, gy, gx, ctx);
   return generic_backward(P, desc->dtype, desc->measure, x, gy, gx, ctx);
@@ -191,6 +208,7 @@ int nfpb200_pool_forward(const nfpb200_desc_t* desc, const void* x, float* gap_x
   if (!x || !gap_x || !gap_nfp) return NFPB200_EINVAL;
   if (misaligned(x)) return NFPB200_EALIGN;
   NFP_PROLOGUE(NFPB200_OP_POOL_FORWARD)
+  if (path == 4) return token_run(P, NFPB200_OP_POOL_FORWARD, x, nullptr, nullptr, nullptr, nullptr, nullptr, gap_x, gap_nfp, ctx);
   if (path == 2) return stream_pool_forward(P, desc->dtype, x, gap_x, gap_nfp, ctx);
   return generic_pool_forward(P, desc->dtype, desc->measure, x, gap_x, gap_nfp, ctx);
 }
@@ -200,6 +218,7 @@ int nfpb200_pool_backward(const nfpb200_desc_t* desc, const void* x, const float
   if (!x || !g_gap_x || !g_gap_nfp || !gx) return NFPB200_EINVAL;
   if (misaligned(x) || misaligned(gx)) return NFPB200_EALIGN;
   NFP_PROLOGUE(NFPB200_OP_POOL_BACKWARD)
+  if (path == 4) return token_run(P, NFPB200_OP_POOL_BACKWARD, x, nullptr, nullptr, gx, g_gap_x, g_gap_nfp, nullptr, nullptr, ctx);
   if (path == 2) return stream_pool_backward(P, desc->dtype, x, g_gap_x, g_gap_nfp, gx, ctx);
   return generic_pool_backward(P, desc->dtype, desc->measure, x, g_gap_x, g_gap_nfp, gx, ctx);
 }

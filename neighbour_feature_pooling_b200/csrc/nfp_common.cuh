@@ -20,6 +20,8 @@ struct KParams {
   int stride, pad, dil, mode;
   int Ho, Wo;
   int similarity, diff_taps, pkind;
+  int layout;           // NFPB200_LAYOUT_*
+  long long x_batch_stride, gx_batch_stride;  // NHWC: elements between images (0 = dense)
   int y_f32;            // NFPB200_FLAG_Y_F32: forward writes y as fp32 although x is bf16
   int x_stable;         // NFPB200_HINT_X_STABLE: x is not an output of the launch that precedes this one
   float eps, p, q;
@@ -83,6 +85,12 @@ int stream_pool_forward(const KParams& P, int dtype, const void* x, float* gap_x
 int stream_pool_backward(const KParams& P, int dtype, const void* x, const float* g_gap_x, const float* g_gap_nfp,
                          void* gx, const LaunchCtx& ctx);
 
+
+// channels-last ("token") tensor-core kernels (bf16, cosine, stride 1, dilation 1, pad = R): nfp_token.cu
+bool token_supported(const KParams& P, int dtype, int measure, int op);
+const char* token_name(const KParams& P);
+int token_run(const KParams& P, int op, const void* x, const void* gy, void* y, void* gx, const float* g_gap_x,
+              const float* g_gap_nfp, float* gap_x, float* gap_nfp, const LaunchCtx& ctx);
 
 // planar kernels (cosine, stride 1, dilation 1, pad = R, any map size; map mode only): nfp_planar.cu
 bool planar_supported(const KParams& P, int dtype, int measure, int op);

@@ -100,8 +100,8 @@ _KERNEL_DTYPES = {torch.float32: _capi.F32, torch.bfloat16: _capi.BF16}
 _X_STABLE_HINT = os.environ.get("NFPB200_X_STABLE_HINT", "1") != "0"
 
 
-def _prepare(x: torch.Tensor):
-    """-> (tensor in a kernel dtype, dtype to return results in)
+def _prepare(x: torch.Tensor, cfg: NFPConfig = None):
+    """-> (tensor in a kernel dtype, dtype to return results in, memory layout the kernels will read)
 
     Under ``torch.autocast('cuda')`` the reference extracts the neighbours with convs in the autocast dtype and then
     runs ``F.cosine_similarity`` (``norm``, ``sum``, ``softmax`` ... for the other measures), which is on autocast's
@@ -120,17 +120,49 @@ def _prepare(x: torch.Tensor):
         raise RuntimeError("NFP kernels compute in fp32; float64 inputs are not supported")
     if x.dtype not in _KERNEL_DTYPES:  # fp16: widen, the kernels accumulate in fp32 anyway
         x = x.float()
+    if cfg is not None and _channels_last_ok(x, cfg):
+        return x, out_dtype, _capi.LAYOUT_NHWC     # consumed in place: no repack copy
     x = x.contiguous()
     if x.data_ptr() % 16:   # a view at an odd storage offset: the kernels move data with 16-byte TMA copies
         x = x.clone()
-    return x, out_dtype
+    return x, out_dtype, _capi.LAYOUT_NCHW
 
 
-def _desc_for(x: torch.Tensor, cfg: NFPConfig) -> _capi.Desc:
+def _is_channels_last_view(x: torch.Tensor) -> bool:
+    """x[b, c, h, w] lives at b*sB + (h*W + w)*C + c: a torch channels_last map, or the (B, C, H, W) VIEW the
+    reference's ViT head makes of the backbone's (B, 1+N, C) token tensor (texture_pooling.py:181-188)."""
     B, C, H, W = x.shape
+    sb, sc, sh, sw = x.stride()
+    return C > 1 and sc == 1 and sw == C and sh == W * C and (B == 1 or sb >= H * W * C) and not x.is_contiguous()
+
+
+def _channels_last_ok(x: torch.Tensor, cfg: NFPConfig) -> bool:
+    """True when the tensor-core channels-last kernels (fused/token_*) take x as it lies in memory."""
+    if x.dtype != torch.bfloat16 or x.dim() != 4 or not _is_channels_last_view(x):
+        return False
+    if x.data_ptr() % 16 or (x.shape[0] > 1 and x.stride(0) % 8):
+        return False
+    if cfg.path == "generic":
+        return False
+    desc = _desc_for(x, cfg, _capi.LAYOUT_NHWC)
+    buf = ctypes.create_string_buffer(64)
+    return _capi.load().nfpb200_describe_path(ctypes.byref(desc), _capi.OP_BACKWARD, buf, 64) == 0
+
+
+def _desc_for(x: torch.Tensor, cfg: NFPConfig, layout: int = 0) -> _capi.Desc:
+    B, C, H, W = x.shape
+    xbs = x.stride(0) if (layout == _capi.LAYOUT_NHWC and B > 1) else 0
     return _capi.make_desc(_KERNEL_DTYPES[x.dtype], B, C, H, W, cfg.R, cfg.stride, cfg.padding,
                            cfg.dilation, cfg.padding_mode, cfg.measure, cfg.similarity,
-                           cfg.difference_taps, cfg.eps, cfg.p, cfg.q_scs, cfg.path)
+                           cfg.difference_taps, cfg.eps, cfg.p, cfg.q_scs, cfg.path, layout=layout,
+                           x_batch_stride=xbs, gx_batch_stride=0)
+
+
+def _empty_like_layout(x: torch.Tensor, layout: int) -> torch.Tensor:
+    if layout == _capi.LAYOUT_NHWC:   # dense channels_last: what a cuDNN NHWC backbone wants back
+        B, C, H, W = x.shape
+        return torch.empty_strided((B, C, H, W), (H * W * C, 1, W * C, C), dtype=x.dtype, device=x.device)
+    return torch.empty_like(x)
 
 
 def _workspace(desc, op, device):
@@ -147,8 +179,8 @@ def _stream(device) -> int:
 
 class _NFPSimilarity(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, cfg, y_f32=False):
-        desc = _desc_for(x, cfg)
+    def forward(ctx, x, cfg, y_f32=False, layout=0):
+        desc = _desc_for(x, cfg, layout)
         Ho, Wo = _capi.output_shape(desc)
         # bf16 x, fp32 map (autocast): the fused kernels write fp32 directly; other paths write bf16 (widened by
         # the caller)
@@ -165,13 +197,14 @@ class _NFPSimilarity(torch.autograd.Function):
         _capi.check(rc, "nfpb200_forward")
         ctx.save_for_backward(x)
         ctx.cfg = cfg
+        ctx.layout = layout
         return y
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gy):
         (x,) = ctx.saved_tensors
-        desc = _desc_for(x, ctx.cfg)
+        desc = _desc_for(x, ctx.cfg, ctx.layout)
         # x is a saved forward activation: whatever NFP kernel precedes this launch on the stream did not write it,
         # so the fused backward may stream it while that kernel drains (NFPB200_HINT_X_STABLE, include/nfp_b200.h).
         # It pays when NFP launches are adjacent on the stream (-1.7 us per backward); after any other kernel there is
@@ -181,19 +214,19 @@ class _NFPSimilarity(torch.autograd.Function):
         gy = gy.to(x.dtype).contiguous()
         if gy.data_ptr() % 16:
             gy = gy.clone()
-        gx = torch.empty_like(x)
+        gx = _empty_like_layout(x, ctx.layout)
         with torch.cuda.device(x.device):
             ws, ws_ptr, ws_n = _workspace(desc, _capi.OP_BACKWARD, x.device)
             rc = _capi.load().nfpb200_backward(ctypes.byref(desc), x.data_ptr(), gy.data_ptr(), gx.data_ptr(),
                                                ws_ptr, ws_n, _stream(x.device))
         _capi.check(rc, "nfpb200_backward")
-        return gx, None, None
+        return gx, None, None, None
 
 
 class _NFPGapPair(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, cfg):
-        desc = _desc_for(x, cfg)
+    def forward(ctx, x, cfg, layout=0):
+        desc = _desc_for(x, cfg, layout)
         B, C = x.shape[:2]
         gap_x = torch.empty((B, C), dtype=torch.float32, device=x.device)
         gap_nfp = torch.empty((B, cfg.out_channels), dtype=torch.float32, device=x.device)
@@ -204,13 +237,14 @@ class _NFPGapPair(torch.autograd.Function):
         _capi.check(rc, "nfpb200_pool_forward")
         ctx.save_for_backward(x)
         ctx.cfg = cfg
+        ctx.layout = layout
         return gap_x, gap_nfp
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_gap_x, g_gap_nfp):
         (x,) = ctx.saved_tensors
-        desc = _desc_for(x, ctx.cfg)
+        desc = _desc_for(x, ctx.cfg, ctx.layout)
         # x is a saved forward activation: whatever NFP kernel precedes this launch on the stream did not write it,
         # so the fused backward may stream it while that kernel drains (NFPB200_HINT_X_STABLE, include/nfp_b200.h).
         # It pays when NFP launches are adjacent on the stream (-1.7 us per backward); after any other kernel there is
@@ -219,14 +253,14 @@ class _NFPGapPair(torch.autograd.Function):
             desc.path |= _capi.HINT_X_STABLE
         g_gap_x = g_gap_x.float().contiguous()
         g_gap_nfp = g_gap_nfp.float().contiguous()
-        gx = torch.empty_like(x)
+        gx = _empty_like_layout(x, ctx.layout)
         with torch.cuda.device(x.device):
             ws, ws_ptr, ws_n = _workspace(desc, _capi.OP_POOL_BACKWARD, x.device)
             rc = _capi.load().nfpb200_pool_backward(ctypes.byref(desc), x.data_ptr(), g_gap_x.data_ptr(),
                                                     g_gap_nfp.data_ptr(), gx.data_ptr(), ws_ptr, ws_n,
                                                     _stream(x.device))
         _capi.check(rc, "nfpb200_pool_backward")
-        return gx, None
+        return gx, None, None
 
 
 def nfp_similarity(x: torch.Tensor, cfg: NFPConfig) -> torch.Tensor:
@@ -237,8 +271,8 @@ def nfp_similarity(x: torch.Tensor, cfg: NFPConfig) -> torch.Tensor:
         _reject_cpu(x)
     if x.dim() == 4:
         _check_geometry(x.shape[2], x.shape[3], cfg)
-    xk, out_dtype = _prepare(x)
-    y = _NFPSimilarity.apply(xk, cfg, out_dtype == torch.float32)
+    xk, out_dtype, layout = _prepare(x, cfg)
+    y = _NFPSimilarity.apply(xk, cfg, out_dtype == torch.float32, layout)
     return y if y.dtype == out_dtype else y.to(out_dtype)
 
 
@@ -248,18 +282,18 @@ def nfp_gap_pair(x: torch.Tensor, cfg: NFPConfig):
         _reject_cpu(x)
     if x.dim() == 4:
         _check_geometry(x.shape[2], x.shape[3], cfg)
-    xk, out_dtype = _prepare(x)
-    gx, gn = _NFPGapPair.apply(xk, cfg)   # both fp32 (the kernels accumulate in fp32)
+    xk, out_dtype, layout = _prepare(x, cfg)
+    gx, gn = _NFPGapPair.apply(xk, cfg, layout)   # both fp32 (the kernels accumulate in fp32)
     # NFP_Pooling.py:27: avgpool(x) keeps the dtype of x (also under autocast); :31: the similarity map's dtype
     return gx.to(x.dtype), gn.to(out_dtype)
 
 
-def describe(x_shape, dtype: torch.dtype, cfg: NFPConfig, op: int = _capi.OP_FORWARD) -> str:
+def describe(x_shape, dtype: torch.dtype, cfg: NFPConfig, op: int = _capi.OP_FORWARD, layout: int = 0) -> str:
     """Name of the kernel path a problem would take (for tests / bench reporting)."""
     B, C, H, W = x_shape
     desc = _capi.make_desc(_KERNEL_DTYPES[dtype], B, C, H, W, cfg.R, cfg.stride, cfg.padding, cfg.dilation,
                            cfg.padding_mode, cfg.measure, cfg.similarity, cfg.difference_taps, cfg.eps,
-                           cfg.p, cfg.q_scs, cfg.path)
+                           cfg.p, cfg.q_scs, cfg.path, layout=layout)
     return _capi.describe_path(desc, op)
 
 

@@ -32,8 +32,30 @@ def test_header_symbols_are_exported():
 
 
 def test_desc_struct_matches_header_layout():
-    # 18 x 4-byte fields, no padding
-    assert ctypes.sizeof(_capi.Desc) == 72
+    # ABI v2: 18 x 4-byte fields, layout + reserved (2 x 4), two 8-byte batch strides; no padding
+    assert ctypes.sizeof(_capi.Desc) == 96
+    assert _capi.Desc.layout.offset == 72 and _capi.Desc.x_batch_stride.offset == 80
+
+
+def test_channels_last_layout_selection():
+    """NHWC descriptors: served by the tensor-core token kernels for bf16 / cosine / pad = R, refused otherwise
+    (the caller repacks to NCHW); batch strides must be multiples of 8 elements (16-byte copies)."""
+    def d(**kw):
+        dd = _desc(**{k: v for k, v in kw.items() if k not in ("dtype", "layout", "xbs")})
+        dd.dtype = kw.get("dtype", _capi.BF16)
+        dd.layout = kw.get("layout", _capi.LAYOUT_NHWC)
+        dd.x_batch_stride = kw.get("xbs", 0)
+        return dd
+    assert _capi.describe_path(d(B=4, C=512), _capi.OP_FORWARD) == "fused/token_7x7_r1"
+    assert _capi.describe_path(d(B=4, C=192, H=14, W=14, xbs=197 * 192), _capi.OP_BACKWARD) == "fused/token_14x14_r1"
+    assert _capi.describe_path(d(B=4, C=960), _capi.OP_POOL_BACKWARD) == "fused/token_7x7_r1"
+    assert _capi.workspace_bytes(d(B=4, C=512), _capi.OP_BACKWARD) == 0
+    lib = _capi.load()
+    n = ctypes.c_size_t()
+    for bad in (d(B=4, C=512, dtype=_capi.F32), d(B=4, C=100), d(B=4, C=64, H=9, W=9), d(B=4, C=512, measure="dot")):
+        assert lib.nfpb200_workspace_bytes(ctypes.byref(bad), _capi.OP_FORWARD, ctypes.byref(n)) == -5
+    assert lib.nfpb200_workspace_bytes(ctypes.byref(d(B=4, C=512, xbs=49 * 512 + 4)), _capi.OP_FORWARD, ctypes.byref(n)) == -7
+    assert lib.nfpb200_workspace_bytes(ctypes.byref(d(B=4, C=512, xbs=8)), _capi.OP_FORWARD, ctypes.byref(n)) == -1
 
 
 def test_output_shape_rule():

@@ -565,3 +565,84 @@ def test_nfp_pooling_respects_customised_layers(cuda_device):
     assert not head2._fusable()
     want2 = x.mean((2, 3)) * head.nfp_proj(2 * NFPPooling(64, R=1, measure="cosine", padding=1)(x).mean((2, 3)))
     assert rel_err(head2(x).detach().cpu(), want2.detach().cpu()) < 1e-6
+
+
+TOKEN_SHAPES = [(5, 64, 7, 7, 1), (3, 512, 7, 7, 1), (2, 960, 7, 7, 1), (3, 192, 14, 14, 1), (2, 256, 14, 14, 1),
+                (6, 512, 2, 2, 1), (4, 64, 4, 4, 1), (3, 128, 7, 7, 2), (2, 64, 14, 14, 2), (300, 64, 7, 7, 1)]
+
+
+@pytest.mark.parametrize("shape", TOKEN_SHAPES, ids=lambda s: "x".join(map(str, s[:4])) + f"_r{s[4]}")
+@pytest.mark.parametrize("mode,similarity", [("reflect", True), ("zeros", True), ("replicate", False)],
+                         ids=["reflect", "zeros", "replicate_dist"])
+def test_channels_last_bf16_without_repack(shape, mode, similarity, cuda_device):
+    """a channels_last bf16 map is consumed where it lies (no .contiguous() repack): the tensor-core
+    fused/token kernels (Gram band and gx = M X on mma.sync, bf16 products exact, fp32 accumulate).  Map and pooled
+    modes against the oracle on the bf16-rounded input, gradient returned channels_last, bit-repeatable."""
+    B, C, H, W, R = shape
+    K = (2 * R + 1) ** 2 - 1
+    gen = torch.Generator().manual_seed(B * 77 + C + H + R)
+    x = torch.randn(B, C, H, W, generator=gen).bfloat16().float()
+    if C % 128 == 0:
+        x = x.relu()
+    x[0, :, 0, 0] = 0.0
+    g = torch.randn(B, K, H, W, generator=gen).bfloat16().float()
+    kw = dict(R=R, measure="cosine", padding=R, padding_mode=mode, similarity=similarity)
+    layer = NFPPooling(C, **kw).to(cuda_device)
+    cfg = layer.config
+    assert NF.describe(shape[:4], torch.bfloat16, cfg, layout=1).startswith("fused/token")
+    y_ref, gx_ref = O.nfp_forward_backward(x.double(), g.double(), **kw)
+    xd = x.to(cuda_device, torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    assert NF._channels_last_ok(xd.detach(), cfg), "expected to be consumed in place"
+    y = layer(xd)
+    y.backward(g.to(cuda_device, torch.bfloat16))
+    assert y.is_contiguous() and y.shape == (B, K, H, W)
+    assert xd.grad.stride() == xd.stride() or H * W == 1, "gradient comes back channels_last"
+    assert rel_err(y.detach().float().cpu(), y_ref) < BF16_TOL
+    assert rel_err(xd.grad.float().cpu(), gx_ref) < BF16_TOL
+    # the NCHW kernels on the same values agree to bf16 rounding, and the token path repeats bit for bit
+    xn = x.to(cuda_device, torch.bfloat16).requires_grad_(True)
+    yn = layer(xn)
+    yn.backward(g.to(cuda_device, torch.bfloat16))
+    assert rel_err(y.detach().float().cpu(), yn.detach().float().cpu()) < 1e-2
+    x2 = xd.detach().clone(memory_format=torch.preserve_format).requires_grad_(True)
+    y2 = layer(x2)
+    y2.backward(g.to(cuda_device, torch.bfloat16))
+    assert torch.equal(y2, y) and torch.equal(x2.grad, xd.grad)
+    # pooled head on the same layout
+    g1 = torch.randn(B, C, generator=gen)
+    g2 = torch.randn(B, K, generator=gen)
+    gy = (g2.double() / (H * W))[:, :, None, None].expand(B, K, H, W).contiguous()
+    y_map, gx_map = O.nfp_forward_backward(x.double(), gy, **kw)
+    y_map, gx_map = torch.as_tensor(np.asarray(y_map)), torch.as_tensor(np.asarray(gx_map))
+    x3 = xd.detach().clone(memory_format=torch.preserve_format).requires_grad_(True)
+    a, n = NF.nfp_gap_pair(x3, cfg)
+    ((a.float() * g1.to(cuda_device)).sum() + (n.float() * g2.to(cuda_device)).sum()).backward()
+    assert rel_err(a.detach().float().cpu(), x.double().mean((2, 3))) < BF16_TOL
+    assert rel_err(n.detach().float().cpu(), y_map.mean((2, 3))) < BF16_TOL
+    assert rel_err(x3.grad.float().cpu(), gx_map + (g1.double() / (H * W))[:, :, None, None]) < BF16_TOL
+
+
+def test_vit_token_view_without_transpose_copy(cuda_device):
+    """The reference's ViT head (texture_pooling.py:181-188) hands NFP `feats[:, 1:].transpose(1, 2).reshape(B, C, H, W)`:
+    a VIEW of the (B, 197, 192) token tensor with strides (197*C, 1, W*C, C).  It is consumed in place (batch stride
+    197*C, data pointer one token in), forward and backward, and the gradient reaches the token tensor."""
+    B, N, C, H, W = 6, 196, 192, 14, 14
+    gen = torch.Generator().manual_seed(5)
+    feats = torch.randn(B, N + 1, C, generator=gen).bfloat16()
+    g = torch.randn(B, 8, H, W, generator=gen).bfloat16()
+    layer = NFPPooling(C, R=1, measure="cosine", padding=1).to(cuda_device)
+    fd = feats.to(cuda_device).requires_grad_(True)
+    fmap = fd[:, 1:].transpose(1, 2).reshape(B, C, H, W)
+    assert fmap.data_ptr() == fd.data_ptr() + C * 2 and fmap.stride() == ((N + 1) * C, 1, W * C, C)   # a view, no copy
+    assert NF._channels_last_ok(fmap.detach(), layer.config)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = layer(fmap)
+    assert y.dtype == torch.float32          # autocast: fp32 similarity map from bf16 tokens
+    y.backward(g.to(cuda_device).float())
+    x_ref = feats[:, 1:].transpose(1, 2).reshape(B, C, H, W).double()
+    y_ref, gx_ref = O.nfp_forward_backward(x_ref, g.double(), R=1, measure="cosine", padding=1)
+    gx_ref = torch.as_tensor(np.asarray(gx_ref))
+    assert rel_err(y.detach().cpu(), y_ref) < 1e-5           # fp32 map of bf16 tokens: only accumulation order differs
+    gtok = fd.grad.float().cpu()
+    assert torch.count_nonzero(gtok[:, 0]) == 0              # the cls token is not part of the map
+    assert rel_err(gtok[:, 1:].transpose(1, 2).reshape(B, C, H, W), gx_ref) < BF16_TOL

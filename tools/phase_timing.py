@@ -21,10 +21,11 @@ ap.add_argument("--shape", default="l4")
 ap.add_argument("--R", type=int, default=1)
 ap.add_argument("--dtype", default="fp32")
 ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--layout", default="nchw")
 args = ap.parse_args()
 C, H, W, _ = SHAPES[args.shape]
 dev = torch.device("cuda:0")
-lb = LayerBench(dev, args.batch, C, H, W, args.R, args.dtype)
+lb = LayerBench(dev, args.batch, C, H, W, args.R, args.dtype, layout=args.layout)
 lib = _capi.load()
 stamps = torch.zeros(8 * 8 * 1024, dtype=torch.int64, device=dev)
 names = {"fwd": ["ready", "passA", "written"], "bwd": ["ready", "passA", "coef", "passB", "drained"]}
@@ -52,7 +53,16 @@ for which, fn in (("fwd", lb.fwd), ("bwd", lb.bwd)):
             col = (s[:, k] - t0) / 1e3
             line += f" {nm}: min {col.min():.1f} med {col.median():.1f} max {col.max():.1f} |"
         print(line)
-        if (s[:, 5] > 0).any():
+        if args.layout == "nhwc":   # token kernels: stamps 0..6 per (CTA, image), durations since the row's own start
+            nm = ["landed", "stencil", "gram", "coef", "Mbuilt", "done"]
+            line = "   per (CTA, image) since its start |"
+            for kk in range(1, 7):
+                ok = s[:, kk] > 0
+                if ok.any():
+                    col = (s[ok, kk] - s[ok, 0]) / 1e3
+                    line += f" {nm[kk - 1]}: {col.median():.2f} ({col.min():.2f}..{col.max():.2f}) |"
+            print(line)
+        elif (s[:, 5] > 0).any():
             line = f"   per-CTA (since its own start; start = {((s[:, 0] - t0) / 1e3).median():.1f} med / {((s[:, 0] - t0) / 1e3).max():.1f} max us after the first CTA) |"
             for k, nm in split_order[which]:
                 col = (s[:, k] - s[:, 0]) / 1e3
