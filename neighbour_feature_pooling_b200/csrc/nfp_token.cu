@@ -58,7 +58,7 @@ struct TokenArgs {
   int B, C;
   long long xbs, gxbs;  // batch strides of x / gx in elements
   int nbuf;             // image buffers in shared memory (1 or 2)
-  int KS;               // channel split of the Gram phase
+  int KS, KSlog;        // channel split of the Gram phase (a power of two) and its log2
   int pad_mode, similarity, y_f32;
   float eps;
   unsigned long long* dbg;  // optional: 8 globaltimer stamps per (CTA, image < 2), see nfpb200_debug_phase_timing
@@ -66,7 +66,7 @@ struct TokenArgs {
 
 #define NFP_TSTAMP(k) do { if (a.dbg && tid == 0 && it < 2) a.dbg[((size_t)blockIdx.x * 2 + it) * 8 + (k)] = globaltimer_ns(); } while (0)
 
-constexpr int kNW = 8, kNT = kNW * 32;
+constexpr int kNW = 16, kNT = kNW * 32;   // 4 warps per SM sub-partition: the MMA / ldmatrix latencies overlap across warps
 constexpr int kSmemPerSM = 227 * 1024;
 constexpr int kMaxKS = 8;
 constexpr int kStgStride = 144;  // bytes per staged gx row: 64 channels + 16 (conflict-free fragment stores)
@@ -110,7 +110,7 @@ struct Geo {
 template <class C, int MODE>
 struct Lay {
   static constexpr bool BWD = (MODE == MODE_BWD || MODE == MODE_POOL_BWD);
-  int tfull, tpart, inv, rn, wd, gp, tabs, gyraw, ggx, mhi, mlo, stg, ytab, xs, total;
+  int tfull, tpart, inv, rn, wd, gp, tabs, gyraw, ggx, mhi, mlo, stg, ytab, eidx, xs, total;
   int t_fv, t_fd, t_q, t_fsrc, t_fdst, t_fptr;
   int gy_stride, x_stride, row_bytes;
   __host__ __device__ Lay(int Cch, int nbuf, int ks) {
@@ -118,11 +118,18 @@ struct Lay {
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 127) & ~127; return r; };
     tfull = take(C::PNV * 4);
-    tpart = take(ks * C::PNV * 4);
     inv = take(C::P * 4);
     rn = take(BWD ? C::P * 4 : 0);
     wd = take(BWD ? C::H * C::RS * 4 : 0);
+    // union: [Gram partial tables | gy-only stencil scratch] are dead once the coefficients exist; the per-warp gx
+    // staging of the last phase lives on top of them
+    const int u0 = o;
+    tpart = take(ks * C::PNV * 4);
     gp = take(BWD ? C::P * C::KK * 4 : 0);
+    const int u1 = o;
+    o = u0;
+    stg = take(BWD ? kNW * 16 * kStgStride : 0);
+    if (o < u1) o = u1;
     tabs = take(BWD ? Tables<C>::BWD_BYTES : Tables<C>::FWD_BYTES);
     if (BWD) {
       t_q = tabs;
@@ -140,8 +147,8 @@ struct Lay {
     ggx = take(MODE == MODE_POOL_BWD ? Cch * 4 : 0);
     mhi = take(BWD ? G::MT * 16 * G::MS : 0);
     mlo = take(BWD ? G::MT * 16 * G::MS : 0);
-    stg = take(BWD ? kNW * 16 * kStgStride : 0);
     ytab = take(MODE == MODE_POOL_FWD ? C::K * C::P * 4 : 0);
+    eidx = take(G::MT * 32 * G::NTN * 4 * 2);  // table entry of every Gram accumulator element (m-tile, lane, n-tile, e)
     row_bytes = Cch * 2;
     x_stride = G::PPAD * row_bytes;
     xs = take(nbuf * x_stride);
@@ -185,27 +192,48 @@ __global__ void __launch_bounds__(kNT, 1) token_kernel(const TokenArgs a, const 
       uint4* z = reinterpret_cast<uint4*>(smem_raw + L.xs + bf * L.x_stride + P * row_bytes);
       for (int i = tid; i < (PPAD - P) * row_bytes / 16; i += NT) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
+    // which per-pixel table entry (p * NV + dy * k + dx) a Gram accumulator element is, -1 = none: depends on the
+    // geometry only, so it is worked out once here instead of per image in the accumulator epilogue
+    {
+      int16_t* ei = reinterpret_cast<int16_t*>(smem_raw + L.eidx);
+      for (int i = tid; i < MT * 32 * NTN * 4; i += NT) {
+        const int e = i & 3, j = (i >> 2) % NTN, ln = (i / (4 * NTN)) & 31, mt = i / (4 * NTN * 32);
+        const int p = mt * 16 + (ln >> 2) + ((e >> 1) << 3), q = mt * 16 + 8 * j + 2 * (ln & 3) + (e & 1);
+        int v = -1;
+        if (p < P && q < P && q >= p) {
+          const int pr = p / W, pc = p - pr * W, qr = q / W, qc = q - qr * W;
+          const int dy = qr - pr, dx = qc - pc;
+          if (dy <= R && dx >= -R && dx <= R && (dy > 0 || dx >= 0)) v = p * NV + dy * k + dx;
+        }
+        ei[i] = (int16_t)v;
+      }
+    }
     if constexpr (BWD) {  // M: the entries outside the band positions written below stay zero
       uint4* z = reinterpret_cast<uint4*>(smem_raw + L.mhi);
-      for (int i = tid; i < (L.stg - L.mhi) / 16; i += NT) z[i] = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = tid; i < 2 * G::MT * 16 * G::MS / 16; i += NT) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
   grid_dependency_wait();
   if (tid == 0) grid_launch_dependents();
 
   const int nmine = (a.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  auto issue = [&](int it) {  // image `it` of this CTA -> buffer it % NBUF (all threads)
+  const int ld_row0 = tid / chunks, ld_ch0 = tid - ld_row0 * chunks, ld_drow = NT / chunks, ld_dch = NT - ld_drow * chunks;
+  auto issue = [&](int it) {  // image `it` of this CTA -> buffer it % NBUF (all threads); two groups: gy, then x
     const int b = blockIdx.x + it * gridDim.x, bf = it % NBUF;
-    const bf16* src = reinterpret_cast<const bf16*>(a.x) + (size_t)b * a.xbs;
-    const uint32_t xb = xs0 + bf * L.x_stride;
-    for (int i = tid; i < P * chunks; i += NT) {
-      const int row = i / chunks, ch = i - row * chunks;
-      cp_async16(xaddr(xb, row, ch), src + (size_t)row * Cch + ch * 8);
-    }
     if constexpr (MODE == MODE_BWD) {
       const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.gy) + (size_t)b * GY_BYTES;
       const uint32_t gd = smem_u32(smem_raw + L.gyraw + bf * L.gy_stride);
       for (int i = tid; i < GY_BYTES / 16; i += NT) cp_async16(gd + i * 16, gsrc + i * 16);
+    }
+    cp_async_commit();
+    const bf16* src = reinterpret_cast<const bf16*>(a.x) + (size_t)b * a.xbs;
+    const uint32_t xb = xs0 + bf * L.x_stride;
+    int row = ld_row0, ch = ld_ch0;
+    while (row < P) {   // (row, chunk) walk in steps of NT chunks, no divisions
+      cp_async16(xaddr(xb, row, ch), src + (size_t)row * Cch + ch * 8);
+      row += ld_drow;
+      ch += ld_dch;
+      if (ch >= chunks) { ch -= chunks; ++row; }
     }
     cp_async_commit();
   };
@@ -217,14 +245,13 @@ __global__ void __launch_bounds__(kNT, 1) token_kernel(const TokenArgs a, const 
     const unsigned char* xbp = smem_raw + L.xs + bf * L.x_stride;
     NFP_TSTAMP(0);
     if (NBUF == 1 || it == 0) issue(it);
-    if (NBUF == 2 && it + 1 < nmine) {
-      issue(it + 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+    const bool ahead = (NBUF == 2 && it + 1 < nmine);
+    if (ahead) issue(it + 1);
+    // groups in flight, oldest first: gy(it), x(it) [, gy(it+1), x(it+1)] -- the upstream gradient first: the gy-only
+    // stencil part below runs while x is still streaming in
+    if (ahead) cp_async_wait<3>(); else cp_async_wait<1>();
     __syncthreads();
-    NFP_TSTAMP(1);  // image landed
+    NFP_TSTAMP(1);  // gradient landed
 
     // ---- backward: the gy-only part of the stencil (as in the NCHW kernels) ---------------------------------------
     if constexpr (BWD) {
@@ -269,12 +296,14 @@ __global__ void __launch_bounds__(kNT, 1) token_kernel(const TokenArgs a, const 
       }
     }
 
-    NFP_TSTAMP(2);  // gy-only stencil part done
+    if (ahead) cp_async_wait<2>(); else cp_async_wait<0>();
+    __syncthreads();
+    NFP_TSTAMP(2);  // gy-only stencil part done, image landed
     // ---- Gram band on the tensor cores: items (m-tile, channel split) over the warps ------------------------------
     {
-      const int kper = Cch / KS;
+      const int kper = Cch >> a.KSlog;
       for (int item = warp; item < MT * KS; item += NW) {
-        const int mt = item / KS, ks = item - mt * KS;
+        const int mt = item >> a.KSlog, ks = item & (KS - 1);
         const int m0 = mt * 16, kbeg = ks * kper, kend = kbeg + kper;
         float acc[NTN][4];
 #pragma unroll
@@ -288,31 +317,55 @@ __global__ void __launch_bounds__(kNT, 1) token_kernel(const TokenArgs a, const 
           const int rr = m0 + 16 * jp + (lane & 7) + ((lane >> 4) << 3);
           brow[jp] = rr < PPAD ? rr : PPAD - 1;
         }
+        // per-lane operand addresses: row base + swizzled 16-byte chunk; fragments of step s+1 are fetched before the
+        // MMAs of step s are issued (two register sets), so ldmatrix latency overlaps the tensor-core work
+        constexpr int NBP = (NTN + 1) / 2;
         const int arow = m0 + (lane & 15);
-        for (int k0 = kbeg; k0 < kend; k0 += 16) {
-          uint32_t af[4];
-          ldmatrix_x4(af, xaddr(xb, arow, (k0 >> 3) + (lane >> 4)));
+        const uint32_t abase = xb + (uint32_t)(arow * row_bytes), ax = (uint32_t)(arow & 7), ac = (uint32_t)(lane >> 4);
+        uint32_t bbase[NBP], bxr[NBP];
 #pragma unroll
-          for (int jp = 0; jp < (NTN + 1) / 2; ++jp) {
-            uint32_t bq[4];
-            ldmatrix_x4(bq, xaddr(xb, brow[jp], (k0 >> 3) + ((lane >> 3) & 1)));
-            mma_bf16(acc[2 * jp], af, bq[0], bq[1]);
-            if (2 * jp + 1 < NTN) mma_bf16(acc[2 * jp + 1], af, bq[2], bq[3]);
+        for (int jp = 0; jp < NBP; ++jp) {
+          bbase[jp] = xb + (uint32_t)(brow[jp] * row_bytes);
+          bxr[jp] = (uint32_t)(brow[jp] & 7);
+        }
+        const uint32_t bc = (uint32_t)((lane >> 3) & 1);
+        auto fetch = [&](int k0, uint32_t (&af)[4], uint32_t (&bq)[NBP][4]) {
+          const uint32_t c0 = (uint32_t)(k0 >> 3);
+          ldmatrix_x4(af, abase + (((c0 + ac) ^ ax) << 4));
+#pragma unroll
+          for (int jp = 0; jp < NBP; ++jp) ldmatrix_x4(bq[jp], bbase[jp] + (((c0 + bc) ^ bxr[jp]) << 4));
+        };
+        auto compute = [&](const uint32_t (&af)[4], const uint32_t (&bq)[NBP][4]) {
+#pragma unroll
+          for (int jp = 0; jp < NBP; ++jp) {
+            mma_bf16(acc[2 * jp], af, bq[jp][0], bq[jp][1]);
+            if (2 * jp + 1 < NTN) mma_bf16(acc[2 * jp + 1], af, bq[jp][2], bq[jp][3]);
+          }
+        };
+        uint32_t af0[4], bq0[NBP][4], af1[4], bq1[NBP][4];
+        fetch(kbeg, af0, bq0);
+        for (int k0 = kbeg; k0 < kend; k0 += 32) {   // two steps per trip (kper is a multiple of 32 or ends on step 0)
+          const bool two = k0 + 16 < kend;
+          if (two) fetch(k0 + 16, af1, bq1);
+          compute(af0, bq0);
+          if (two) {
+            if (k0 + 32 < kend) fetch(k0 + 32, af0, bq0);
+            compute(af1, bq1);
           }
         }
         // accumulator entries that are forward window directions -> this split's partial table
         float* tp = tpart + ks * PNV;
+        const int16_t* ei = reinterpret_cast<const int16_t*>(smem_raw + L.eidx) + (mt * 32 + lane) * (NTN * 4);
 #pragma unroll
-        for (int j = 0; j < NTN; ++j)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int p = m0 + g8 + ((e >> 1) << 3), q = m0 + 8 * j + 2 * t4 + (e & 1);
-            if (p < P && q < P && q >= p) {
-              const int pr = p / W, pc = p - pr * W, qr = q / W, qc = q - qr * W;
-              const int dy = qr - pr, dx = qc - pc;
-              if (dy <= R && dx >= -R && dx <= R && (dy > 0 || dx >= 0)) tp[p * NV + dy * k + dx] = acc[j][e];
-            }
-          }
+        for (int j = 0; j < NTN; ++j) {
+          const uint2 w = *reinterpret_cast<const uint2*>(ei + 4 * j);
+          const int i0 = (int)(int16_t)(w.x & 0xffffu), i1 = (int)(int16_t)(w.x >> 16);
+          const int i2 = (int)(int16_t)(w.y & 0xffffu), i3 = (int)(int16_t)(w.y >> 16);
+          if (i0 >= 0) tp[i0] = acc[j][0];
+          if (i1 >= 0) tp[i1] = acc[j][1];
+          if (i2 >= 0) tp[i2] = acc[j][2];
+          if (i3 >= 0) tp[i3] = acc[j][3];
+        }
       }
     }
     __syncthreads();
@@ -442,23 +495,29 @@ __global__ void __launch_bounds__(kNT, 1) token_kernel(const TokenArgs a, const 
           }
           acc[j][0] = i0; acc[j][1] = i1; acc[j][2] = i0; acc[j][3] = i1;
         }
+        const uint32_t bch = (uint32_t)((ch0 >> 3) + (lane >> 4));
 #pragma unroll
         for (int kk = 0; kk < KTN; ++kk) {
           const int kt = mt - HT + kk;
           if (kt < 0 || kt >= MT) continue;
-          uint32_t ahi[4], alo[4];
+          uint32_t ahi[4], alo[4], bx[4][4];
           const uint32_t moff = (uint32_t)((m0 + (lane & 15)) * MS + kk * 32 + ((lane >> 4) << 4));
+          const int brow = 16 * kt + (lane & 7) + (((lane >> 3) & 1) << 3);
+          const uint32_t bb = xb + (uint32_t)(brow * row_bytes), bxr = (uint32_t)(brow & 7);
+          // all six operand fetches of the k-tile go out before its sixteen MMAs
           ldmatrix_x4(ahi, mhi_a + moff);
           ldmatrix_x4(alo, mlo_a + moff);
-          const int brow = 16 * kt + (lane & 7) + (((lane >> 3) & 1) << 3);
+#pragma unroll
+          for (int np = 0; np < 4; ++np) ldmatrix_x4_trans(bx[np], bb + (((bch + 2 * np) ^ bxr) << 4));
 #pragma unroll
           for (int np = 0; np < 4; ++np) {
-            uint32_t bx[4];
-            ldmatrix_x4_trans(bx, xaddr(xb, brow, ((ch0 + np * 16) >> 3) + (lane >> 4)));
-            mma_bf16(acc[2 * np], ahi, bx[0], bx[1]);
-            mma_bf16(acc[2 * np], alo, bx[0], bx[1]);
-            mma_bf16(acc[2 * np + 1], ahi, bx[2], bx[3]);
-            mma_bf16(acc[2 * np + 1], alo, bx[2], bx[3]);
+            mma_bf16(acc[2 * np], ahi, bx[np][0], bx[np][1]);
+            mma_bf16(acc[2 * np + 1], ahi, bx[np][2], bx[np][3]);
+          }
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {
+            mma_bf16(acc[2 * np], alo, bx[np][0], bx[np][1]);
+            mma_bf16(acc[2 * np + 1], alo, bx[np][2], bx[np][3]);
           }
         }
         // fragments -> bf16 -> staging (row stride 144 B: conflict-free) -> 128-byte row segments of gx
@@ -498,10 +557,8 @@ Plan plan_for(const KParams& P) {
   using G = Geo<C>;
   if (P.C % 64 || P.C < 64) return pl;             // swizzle granule: 8 chunks of 8 channels
   if ((C::K * C::P * 2) % 16) return pl;           // upstream-gradient rows are fetched with 16-byte copies
-  int ks = kNW / G::MT;
-  if (ks < 1) ks = 1;
-  if (ks > kMaxKS) ks = kMaxKS;
-  while (ks > 1 && (P.C % ks || (P.C / ks) % 16)) --ks;
+  int ks = 1;
+  while (ks < kMaxKS && ks * G::MT < kNW && P.C % (2 * ks) == 0 && (P.C / (2 * ks)) % 16 == 0) ks *= 2;
   pl.KS = ks;
   for (int nbuf = 2; nbuf >= 1 && !pl.ok; --nbuf) {
     Lay<C, MODE> L(P.C, nbuf, ks);
@@ -519,6 +576,8 @@ int launch_mode(const KParams& P, TokenArgs a, cudaStream_t stream) {
   if (!pl.ok) return NFPB200_EUNSUPPORTED;
   a.nbuf = pl.nbuf;
   a.KS = pl.KS;
+  a.KSlog = 0;
+  while ((1 << a.KSlog) < pl.KS) ++a.KSlog;
   auto kern = token_kernel<C, MODE>;
   constexpr int kMaxDev = 64;
   static int sm_count[kMaxDev] = {0};
