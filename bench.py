@@ -64,7 +64,9 @@ def parse_args():
     ap.add_argument("--no-sweep", action="store_true", help="skip the table over the other configs[1] cases")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the ResNet18+NFP training-step measurement")
-    ap.add_argument("--train-config", default="eurosat", choices=["eurosat", "ucmerced"])
+    ap.add_argument("--train-config", default="eurosat", choices=["eurosat", "ucmerced", "gtos_mbv3", "plantvillage_vit"])
+    ap.add_argument("--train-more", default="gtos_mbv3,plantvillage_vit,ucmerced",
+                    help="further BASELINE.json configs measured as training steps (comma separated, '' = none)")
     ap.add_argument("--train-batch", type=int, default=256, help="images per GPU per training step")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline budget (seconds of CPU work)")
@@ -633,7 +635,7 @@ def main():
                     n = max(min(args.steps, 200), 60)
                     tt = s.timed(s.step, n, 5, sampler, "sweep") / n
                     tf = s.timed(s.fwd, n, 5, sampler, "sweep") / n
-                    tb = s.timed(s.bwd, n, 5, sampler, "sweep") / n
+                    tb = s.timed(s.bwd_conservative, n, 5, sampler, "sweep") / n
                     fb, bb = algorithmic_bytes(B, c, h, w, r, s.esz)
                     sweep.append({"workload": workload_name(B, c, h, w, r, dt) + (" channels-last" if lay == "nhwc" else ""),
                                   "maps_per_s": B / tt,
@@ -653,6 +655,20 @@ def main():
             sampler.tag = None
             if rank == 0 and world == 1 and not args.no_cpu_baseline:
                 train["cpu_baseline"] = bench_train.run_cpu_baseline(args.train_config)
+            # the other BASELINE.json configs: [3] MobileNetV3+NFP (64 per GPU = 512 over 8), [4] ViT-Tiny+NFP bf16,
+            # [0] ResNet18+NFP batch 8 3x224x224 (beside the reference's CPU time for exactly that case)
+            more = []
+            for name in [c for c in args.train_more.split(",") if c]:
+                cfgm = bench_train.CONFIGS[name]
+                bsz = 8 if name == "ucmerced" else cfgm.get("batch", args.train_batch)
+                sampler.tag = "train"
+                r = bench_train.run_gpu(name, bsz, args.train_steps, 5)
+                sampler.tag = None
+                r["config"] = name
+                if name == "ucmerced" and rank == 0 and world == 1 and not args.no_cpu_baseline:
+                    r["cpu_baseline"] = bench_train.run_cpu_baseline("ucmerced", batch=8, steps=2)
+                more.append(r)
+            train["more_configs"] = more
         except Exception as e:  # e.g. torchvision missing: report it, keep the layer numbers
             sampler.tag = None
             train = {"unavailable": repr(e)[:300]}

@@ -33,6 +33,14 @@ CONFIGS = {  # BASELINE.json configs[2] and configs[0]; `raw` = the dtype the da
                     name="ResNet18+NFP EuroSAT-shaped 13x64x64 (16-bit bands), 10 classes (layer4 map 512x2x2)"),
     "ucmerced": dict(in_chans=3, size=224, classes=21, raw=torch.uint8, raw_max=255.0,
                      name="ResNet18+NFP UCMerced-shaped 3x224x224 (8-bit RGB), 21 classes (layer4 map 512x7x7)"),
+    # BASELINE.json configs[3]: MobileNetV3 + NFP head (models/texture_pooling.py:191-207), GTOS-Mobile-shaped, 31 classes;
+    # global batch 512 over 8 GPUs = 64 per GPU
+    "gtos_mbv3": dict(arch="mbv3", feat=960, in_chans=3, size=224, classes=31, raw=torch.uint8, raw_max=255.0, batch=64,
+                      name="MobileNetV3-large+NFP GTOS-Mobile-shaped 3x224x224, 31 classes (last-stage map 960x7x7)"),
+    # BASELINE.json configs[4]: ViT-Tiny + NFP over the 14x14x192 token grid (models/texture_pooling.py:169-189), bf16
+    "plantvillage_vit": dict(arch="vit", feat=192, in_chans=3, size=224, classes=38, raw=torch.uint8, raw_max=255.0,
+                             batch=64, name="ViT-Tiny/16+NFP PlantVillage-shaped 3x224x224, 38 classes "
+                                            "(token grid 14x14x192, consumed as the reference's transpose/reshape VIEW)"),
 }
 
 
@@ -64,9 +72,54 @@ class ResNet18_NFPPooling(nn.Module):
         return self.fc(self.pool(self.backbone(x)))
 
 
+class MobileNetV3_NFPPooling(nn.Module):
+    """models/texture_pooling.py:191-207 with torchvision's mobilenet_v3_large().features standing in for timm's
+    mobilenetv3_large_100 forward_features (same 960 x 7 x 7 last-stage map; random init)."""
+
+    def __init__(self, num_classes, pool):
+        super().__init__()
+        import torchvision
+        self.backbone = torchvision.models.mobilenet_v3_large(weights=None).features
+        self.pool = pool
+        self.fc = nn.Linear(960, num_classes)
+
+    def forward(self, x):
+        return self.fc(self.pool(self.backbone(x)))
+
+
+class ViTTiny_NFPPooling(nn.Module):
+    """models/texture_pooling.py:169-189 with torchvision's VisionTransformer(224, 16, 12 layers, 3 heads, 192, 768)
+    standing in for timm's vit_tiny_patch16_224 forward_features: tokens (B, 197, 192) -> drop the class token ->
+    transpose(1, 2).reshape(B, C, H, W) (a VIEW: channels-last memory) -> nfp_pooling -> fc."""
+
+    def __init__(self, num_classes, pool):
+        super().__init__()
+        import torchvision
+        self.backbone = torchvision.models.VisionTransformer(image_size=224, patch_size=16, num_layers=12, num_heads=3,
+                                                             hidden_dim=192, mlp_dim=768, num_classes=1)
+        self.backbone.heads = nn.Identity()
+        self.pool = pool
+        self.fc = nn.Linear(192, num_classes)
+
+    def forward_features(self, x):
+        vt = self.backbone
+        x = vt._process_input(x)
+        x = torch.cat([vt.class_token.expand(x.shape[0], -1, -1), x], dim=1)
+        return vt.encoder(x)
+
+    def forward(self, x):
+        feats = self.forward_features(x)
+        patch_tokens = feats[:, 1:]
+        B, N, C = patch_tokens.shape
+        H = W = int(N ** 0.5)
+        fmap = patch_tokens.transpose(1, 2).reshape(B, C, H, W)
+        return self.fc(self.pool(fmap))
+
+
 def make_model(cfg, device, impl="b200"):
-    Params = {"num_ftrs": {"resnet18": 512}, "Model_name": "resnet18", "Dataset": "synthetic",
-              "num_classes": {"synthetic": cfg["classes"]}, "input_size": cfg["size"] // 32}
+    arch, feat = cfg.get("arch", "resnet18"), cfg.get("feat", 512)
+    Params = {"num_ftrs": {arch: feat}, "Model_name": arch, "Dataset": "synthetic",
+              "num_classes": {"synthetic": cfg["classes"]}, "input_size": cfg["size"] // 32 if arch != "vit" else 14}
     if impl == "b200":
         import neighbour_feature_pooling_b200 as nfpb
         pool = nfpb.nfp_pooling(Params=Params)
@@ -81,12 +134,16 @@ def make_model(cfg, device, impl="b200"):
             class RefPool(nn.Module):
                 def __init__(self):
                     super().__init__()
-                    self.nfp_layer = ConvFormCosineNFP(512, R=1, padding=1)
-                    self.nfp_proj = nn.Linear(8, 512)
+                    self.nfp_layer = ConvFormCosineNFP(feat, R=1, padding=1)
+                    self.nfp_proj = nn.Linear(8, feat)
 
                 def forward(self, x):
                     return x.mean((2, 3)) * self.nfp_proj(self.nfp_layer(x).mean((2, 3)))
             pool = RefPool()
+    if arch == "mbv3":
+        return MobileNetV3_NFPPooling(cfg["classes"], pool).to(device)
+    if arch == "vit":
+        return ViTTiny_NFPPooling(cfg["classes"], pool).to(device)
     return ResNet18_NFPPooling(cfg["classes"], cfg["in_chans"], pool).to(device)
 
 
@@ -156,6 +213,8 @@ def run_gpu(config="eurosat", batch=256, steps=20, warmup=5, amp=True, use_graph
         return loss
 
     graph, graph_note, static_loss = None, None, None
+    from neighbour_feature_pooling_b200 import functional as _NF
+    _NF.PATH_TRACE = set()
     with torch.cuda.stream(side):
         sx.copy_(hx[0], non_blocking=True)
         sy.copy_(hy[0], non_blocking=True)
@@ -163,6 +222,7 @@ def run_gpu(config="eurosat", batch=256, steps=20, warmup=5, amp=True, use_graph
             train_step(sx, sy)
     main.wait_stream(side)
     torch.cuda.synchronize(dev)
+    nfp_paths, _NF.PATH_TRACE = sorted(_NF.PATH_TRACE), None
     if use_graph:
         try:
             graph = torch.cuda.CUDAGraph()
@@ -212,8 +272,10 @@ def run_gpu(config="eurosat", batch=256, steps=20, warmup=5, amp=True, use_graph
            "dtype": "bf16 autocast (NFP kernels: bf16 I/O, fp32 accumulate)" if amp else "fp32",
            "parallelism": f"DDP over NCCL, dp{world}, weak scaling" if world > 1 else "single GPU",
            "optimizer": "Adam(lr=1e-4), CrossEntropy(label_smoothing=0.05)",
-           "backbone": "torchvision resnet18 (random init; timm absent), channels_last",
-           "cuda_graph": graph is not None,
+           "backbone": {"resnet18": "torchvision resnet18", "mbv3": "torchvision mobilenet_v3_large().features",
+                        "vit": "torchvision VisionTransformer(224, 16, 12, 3, 192, 768)"}[cfg.get("arch", "resnet18")]
+                       + " (random init; timm absent), channels_last",
+           "cuda_graph": graph is not None, "nfp_kernel_paths": nfp_paths,
            "h2d_bytes_per_step": hx[0].numel() * hx[0].element_size() + hy[0].numel() * 8, "final_loss": lossv, "data": "synthetic"}
     if graph_note:
         out["cuda_graph_error"] = graph_note

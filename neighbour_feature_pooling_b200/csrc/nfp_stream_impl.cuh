@@ -884,7 +884,9 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
       }
     }
   }
-  if (BWD && lane == 0) bulk_wait_all();
+  // shared memory must outlive the bulk stores' READS only; their global writes are complete (and visible to the
+  // next grid) when this grid completes
+  if (BWD && lane == 0) bulk_wait_read<0>();
   img = 0;
   NFP_STAMP(4);  // stores drained
 #undef NFP_OFF

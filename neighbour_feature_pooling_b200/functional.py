@@ -97,6 +97,16 @@ def _reject_cpu(x: torch.Tensor):
 
 
 _KERNEL_DTYPES = {torch.float32: _capi.F32, torch.bfloat16: _capi.BF16}
+# diagnostics: when a set is installed here (bench_train.py does during its eager warm-up), every forward records the
+# kernel path it takes ("fused/token_7x7_r1 bf16 pool", ...)
+PATH_TRACE = None
+
+
+def _trace(desc, op, what):
+    if PATH_TRACE is not None:
+        PATH_TRACE.add(f"{_capi.describe_path(desc, op)} {'bf16' if desc.dtype == _capi.BF16 else 'f32'} "
+                       f"{'channels-last' if desc.layout else 'nchw'} {what}")
+
 _X_STABLE_HINT = os.environ.get("NFPB200_X_STABLE_HINT", "1") != "0"
 
 
@@ -122,6 +132,14 @@ def _prepare(x: torch.Tensor, cfg: NFPConfig = None):
         x = x.float()
     if cfg is not None and _channels_last_ok(x, cfg):
         return x, out_dtype, _capi.LAYOUT_NHWC     # consumed in place: no repack copy
+    if (cfg is not None and x.dtype == torch.float32 and x.dim() == 4 and torch.is_autocast_enabled("cuda")
+            and torch.get_autocast_dtype("cuda") == torch.bfloat16 and _is_channels_last_view(x)):
+        # fp32 channels-last map under bf16 autocast (a ViT's final LayerNorm emits fp32 tokens): the reference's
+        # extraction convs would round it to bf16 (nfp.py:152-153); doing the same costs one cast kernel (4 B in,
+        # 2 B out per element) instead of an NCHW repack (4 B in, 4 B out) and keeps the tensor-core path
+        xb = x.to(torch.bfloat16)
+        if _channels_last_ok(xb, cfg):
+            return xb, out_dtype, _capi.LAYOUT_NHWC
     x = x.contiguous()
     if x.data_ptr() % 16:   # a view at an odd storage offset: the kernels move data with 16-byte TMA copies
         x = x.clone()
@@ -190,6 +208,7 @@ class _NFPSimilarity(torch.autograd.Function):
             desc.path |= _capi.FLAG_Y_F32
         y = torch.empty((x.shape[0], cfg.out_channels, Ho, Wo), dtype=torch.float32 if y_f32 else x.dtype,
                         device=x.device)
+        _trace(desc, _capi.OP_FORWARD, "map")
         with torch.cuda.device(x.device):
             ws, ws_ptr, ws_n = _workspace(desc, _capi.OP_FORWARD, x.device)
             rc = _capi.load().nfpb200_forward(ctypes.byref(desc), x.data_ptr(), y.data_ptr(), ws_ptr, ws_n,
@@ -230,6 +249,7 @@ class _NFPGapPair(torch.autograd.Function):
         B, C = x.shape[:2]
         gap_x = torch.empty((B, C), dtype=torch.float32, device=x.device)
         gap_nfp = torch.empty((B, cfg.out_channels), dtype=torch.float32, device=x.device)
+        _trace(desc, _capi.OP_POOL_FORWARD, "pooled head")
         with torch.cuda.device(x.device):
             ws, ws_ptr, ws_n = _workspace(desc, _capi.OP_POOL_FORWARD, x.device)
             rc = _capi.load().nfpb200_pool_forward(ctypes.byref(desc), x.data_ptr(), gap_x.data_ptr(),

@@ -646,3 +646,30 @@ def test_vit_token_view_without_transpose_copy(cuda_device):
     gtok = fd.grad.float().cpu()
     assert torch.count_nonzero(gtok[:, 0]) == 0              # the cls token is not part of the map
     assert rel_err(gtok[:, 1:].transpose(1, 2).reshape(B, C, H, W), gx_ref) < BF16_TOL
+
+
+def test_fp32_tokens_under_autocast_take_the_token_kernels(cuda_device):
+    """A ViT's final LayerNorm emits fp32 tokens under bf16 autocast; the reference's extraction convs round them to
+    bf16 (nfp.py:152-153).  The drop-in does the same (one cast instead of an NCHW repack) and stays on the
+    channels-last tensor-core path; the map comes back fp32, the gradient fp32."""
+    B, N, C, H, W = 3, 196, 192, 14, 14
+    gen = torch.Generator().manual_seed(9)
+    feats = torch.randn(B, N + 1, C, generator=gen)
+    g = torch.randn(B, 8, H, W, generator=gen)
+    layer = NFPPooling(C, R=1, measure="cosine", padding=1).to(cuda_device)
+    fd = feats.to(cuda_device).requires_grad_(True)
+    fmap = fd[:, 1:].transpose(1, 2).reshape(B, C, H, W)
+    NF.PATH_TRACE = set()
+    try:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = layer(fmap)
+    finally:
+        paths, NF.PATH_TRACE = NF.PATH_TRACE, None
+    assert paths == {"fused/token_14x14_r1 bf16 channels-last map"}
+    assert y.dtype == torch.float32
+    y.backward(g.to(cuda_device))
+    assert fd.grad.dtype == torch.float32
+    xq = feats[:, 1:].transpose(1, 2).reshape(B, C, H, W).bfloat16().double()     # what the reference's convs see
+    y_ref, gx_ref = O.nfp_forward_backward(xq, g.double(), R=1, measure="cosine", padding=1)
+    assert rel_err(y.detach().cpu(), y_ref) < 1e-5
+    assert rel_err(fd.grad[:, 1:].transpose(1, 2).reshape(B, C, H, W).cpu(), gx_ref) < BF16_TOL
