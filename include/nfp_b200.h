@@ -180,6 +180,21 @@ int nfpb200_pool_backward(const nfpb200_desc_t* desc, const void* x, const float
                           const float* g_gap_nfp, void* gx,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- fused nfp_pooling head (NFP_Pooling.py:25-36), one launch each way ---------------------------------------
+ *   out (B, C) = GAP(x) * (proj_w . GAP(NFP(x)) + proj_b)        proj_w (C, K) fp32 row-major = nfp_proj.weight,
+ *                                                                 proj_b (C) fp32 = nfp_proj.bias (NULL = none)
+ * The forward also returns gap_x (B, C) and gap_nfp (B, K) (fp32): the backward reads them back, and the caller needs
+ * them for the parameter gradients (d proj_w = (g_out * gap_x)^T gap_nfp, d proj_b = sum_b g_out * gap_x), which stay
+ * on the caller's side.  Served by the fused NCHW kernels (cosine, pad = R, stride 1, shapes of the streaming path);
+ * nfpb200_head_supported() returns NFPB200_OK when both directions are, NFPB200_EUNSUPPORTED otherwise -- then compose
+ * nfpb200_pool_forward / _backward with the projection on the caller's side. */
+int nfpb200_head_supported(const nfpb200_desc_t* desc);
+int nfpb200_head_forward(const nfpb200_desc_t* desc, const void* x, const float* proj_w, const float* proj_b, float* out,
+                         float* gap_x, float* gap_nfp, void* stream);
+/* gx = d loss / dx given g_out = d loss / d out (B, C) fp32 and the forward's gap_x / gap_nfp. */
+int nfpb200_head_backward(const nfpb200_desc_t* desc, const void* x, const float* proj_w, const float* proj_b,
+                          const float* gap_x, const float* gap_nfp, const float* g_out, void* gx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

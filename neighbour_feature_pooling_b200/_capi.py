@@ -35,7 +35,7 @@ EXPORTS = (
     "nfpb200_abi_version", "nfpb200_status_string", "nfpb200_output_shape",
     "nfpb200_workspace_bytes", "nfpb200_describe_path", "nfpb200_launch_count",
     "nfpb200_forward", "nfpb200_backward", "nfpb200_pool_forward", "nfpb200_pool_backward",
-    "nfpb200_debug_phase_timing",
+    "nfpb200_debug_phase_timing", "nfpb200_head_supported", "nfpb200_head_forward", "nfpb200_head_backward",
 )
 
 
@@ -99,6 +99,12 @@ def load():
         lib.nfpb200_pool_backward.argtypes = [dp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
         lib.nfpb200_debug_phase_timing.restype = ctypes.c_int
         lib.nfpb200_debug_phase_timing.argtypes = [vp]
+        lib.nfpb200_head_supported.restype = ctypes.c_int
+        lib.nfpb200_head_supported.argtypes = [dp]
+        lib.nfpb200_head_forward.restype = ctypes.c_int
+        lib.nfpb200_head_forward.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp]
+        lib.nfpb200_head_backward.restype = ctypes.c_int
+        lib.nfpb200_head_backward.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, vp]
         got = lib.nfpb200_abi_version()
         if got != ABI_VERSION:
             raise RuntimeError(f"libnfp_b200.so ABI version {got}, host code expects {ABI_VERSION}; rebuild")

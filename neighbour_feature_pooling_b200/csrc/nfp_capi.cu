@@ -223,4 +223,52 @@ int nfpb200_pool_backward(const nfpb200_desc_t* desc, const void* x, const float
   return generic_pool_backward(P, desc->dtype, desc->measure, x, g_gap_x, g_gap_nfp, gx, ctx);
 }
 
+// ---- fused nfp_pooling head -------------------------------------------------------------------------------------
+static int head_path(const nfpb200_desc_t* desc, const KParams& P, int pool_op) {
+  if (P.layout == NFPB200_LAYOUT_NHWC) return NFPB200_EUNSUPPORTED;
+  const int want = desc->path & ~kPathFlags;
+  if (want == NFPB200_PATH_GENERIC) return NFPB200_EUNSUPPORTED;
+  return stream_head_supported(P, desc->dtype, desc->measure, pool_op) ? 2 : NFPB200_EUNSUPPORTED;
+}
+
+int nfpb200_head_supported(const nfpb200_desc_t* desc) {
+  KParams P;
+  int rc = make_params(desc, &P);
+  if (rc) return rc;
+  rc = head_path(desc, P, NFPB200_OP_POOL_FORWARD);
+  if (rc < 0) return rc;
+  rc = head_path(desc, P, NFPB200_OP_POOL_BACKWARD);
+  return rc < 0 ? rc : NFPB200_OK;
+}
+
+int nfpb200_head_forward(const nfpb200_desc_t* desc, const void* x, const float* proj_w, const float* proj_b, float* out,
+                         float* gap_x, float* gap_nfp, void* stream) {
+  if (!x || !proj_w || !out || !gap_x || !gap_nfp) return NFPB200_EINVAL;
+  if (misaligned(x) || misaligned(proj_w)) return NFPB200_EALIGN;
+  KParams P;
+  int rc = make_params(desc, &P);
+  if (rc) return rc;
+  rc = check_device();
+  if (rc) return rc;
+  rc = head_path(desc, P, NFPB200_OP_POOL_FORWARD);
+  if (rc < 0) return rc;
+  LaunchCtx ctx{(cudaStream_t)stream, nullptr, 0};
+  return stream_head_forward(P, desc->dtype, x, proj_w, proj_b, out, gap_x, gap_nfp, ctx);
+}
+
+int nfpb200_head_backward(const nfpb200_desc_t* desc, const void* x, const float* proj_w, const float* proj_b,
+                          const float* gap_x, const float* gap_nfp, const float* g_out, void* gx, void* stream) {
+  if (!x || !proj_w || !gap_x || !gap_nfp || !g_out || !gx) return NFPB200_EINVAL;
+  if (misaligned(x) || misaligned(gx) || misaligned(proj_w)) return NFPB200_EALIGN;
+  KParams P;
+  int rc = make_params(desc, &P);
+  if (rc) return rc;
+  rc = check_device();
+  if (rc) return rc;
+  rc = head_path(desc, P, NFPB200_OP_POOL_BACKWARD);
+  if (rc < 0) return rc;
+  LaunchCtx ctx{(cudaStream_t)stream, nullptr, 0};
+  return stream_head_backward(P, desc->dtype, x, proj_w, proj_b, gap_x, gap_nfp, g_out, gx, ctx);
+}
+
 }  // extern "C"

@@ -86,6 +86,12 @@ int stream_pool_backward(const KParams& P, int dtype, const void* x, const float
                          void* gx, const LaunchCtx& ctx);
 
 
+bool stream_head_supported(const KParams& P, int dtype, int measure, int op);
+int stream_head_forward(const KParams& P, int dtype, const void* x, const float* proj_w, const float* proj_b, float* out,
+                        float* gap_x, float* gap_nfp, const LaunchCtx& ctx);
+int stream_head_backward(const KParams& P, int dtype, const void* x, const float* proj_w, const float* proj_b,
+                         const float* gap_x, const float* gap_nfp, const float* g_out, void* gx, const LaunchCtx& ctx);
+
 // channels-last ("token") tensor-core kernels (bf16, cosine, stride 1, dilation 1, pad = R): nfp_token.cu
 bool token_supported(const KParams& P, int dtype, int measure, int op);
 const char* token_name(const KParams& P);

@@ -92,6 +92,27 @@ int stream_pool_forward(const KParams& P, int dtype, const void* x, float* gap_x
   a.x = x; a.gap_x = gap_x; a.gap_nfp = gap_nfp;
   return run(P, dtype, stream::MODE_POOL_FWD, a, ctx.stream);
 }
+// fused nfp_pooling head on the ring kernels (the cluster-split experiment does not carry it)
+bool stream_head_supported(const KParams& P, int dtype, int measure, int op) {
+  return stream_supported(P, dtype, measure, op) && !split_ok(P, dtype, op_mode(op)) && P.K % 4 == 0;
+}
+int stream_head_forward(const KParams& P, int dtype, const void* x, const float* proj_w, const float* proj_b, float* out,
+                        float* gap_x, float* gap_nfp, const LaunchCtx& ctx) {
+  stream::StreamArgs a{};
+  a.x = x; a.gap_x = gap_x; a.gap_nfp = gap_nfp;
+  a.proj_w = proj_w; a.proj_b = proj_b; a.head_out = out;
+  return run(P, dtype, stream::MODE_POOL_FWD, a, ctx.stream);
+}
+int stream_head_backward(const KParams& P, int dtype, const void* x, const float* proj_w, const float* proj_b,
+                         const float* gap_x, const float* gap_nfp, const float* g_out, void* gx, const LaunchCtx& ctx) {
+  stream::StreamArgs a{};
+  a.x = x; a.gx = gx;
+  a.gap_x = const_cast<float*>(gap_x); a.gap_nfp = const_cast<float*>(gap_nfp);   // read-only here: the forward's results
+  a.proj_w = proj_w; a.proj_b = proj_b; a.head_gout = g_out;
+  a.x_early = P.x_stable;
+  a.ggx_tma = 0;
+  return run(P, dtype, stream::MODE_POOL_BWD, a, ctx.stream);
+}
 int stream_pool_backward(const KParams& P, int dtype, const void* x, const float* g_gap_x, const float* g_gap_nfp,
                          void* gx, const LaunchCtx& ctx) {
   stream::StreamArgs a{};

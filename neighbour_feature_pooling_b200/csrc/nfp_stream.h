@@ -18,6 +18,11 @@ struct StreamArgs {
   const float* g_gap_nfp;
   float* gap_x;
   float* gap_nfp;
+  // fused nfp_pooling head (NFP_Pooling.py:31-35): out = GAP(x) * (proj_w GAP(NFP(x)) + proj_b)
+  const float* proj_w;     // (C, K) fp32, null = plain pooled mode
+  const float* proj_b;     // (C) fp32 or null
+  float* head_out;         // forward: (B, C) fp32
+  const float* head_gout;  // backward: d loss / d out (B, C) fp32; gap_x / gap_nfp then hold the forward's saved results
   int B, C;
   int CC;        // channels per chunk (a whole number of group pairs, divides C)
   int NCH;       // chunks per image

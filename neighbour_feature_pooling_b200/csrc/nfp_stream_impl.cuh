@@ -305,12 +305,57 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
       const int par = img & 1;
       const unsigned char* g = smem_raw + L.gyraw + par * GY_STRIDE;
       if constexpr (POOLED) {
-        // d GAP(y) / dy: the same value on every pixel of a tap plane
-        if (tid < K) reinterpret_cast<float*>(smem_raw + L.gyraw)[tid] = a.g_gap_nfp[(size_t)b * K + tid] * (1.f / (float)P);
+        bool head_done = false;
         if constexpr (MODE == MODE_POOL_BWD) {
-          if (!a.ggx_tma) {  // rows not 16-byte aligned / sized: no bulk copy, stage them with plain loads
+          if (a.proj_w) {
+            // fused head backward (NFP_Pooling.py:31-35): from d loss / d out, the forward's GAP(x) and GAP(NFP(x)):
+            //   d/d GAP(x)[c]      = g_out[c] * (proj_w[c] . gnfp + proj_b[c])
+            //   d/d GAP(NFP(x))[n] = sum_c g_out[c] * GAP(x)[c] * proj_w[c][n]      (fixed-order block reduction)
+            head_done = true;
             float* gs = reinterpret_cast<float*>(smem_raw + L.ggx) + (img & 1) * a.C;
-            for (int i = tid; i < a.C; i += NT) gs[i] = a.g_gap_x[(size_t)b * a.C + i];
+            float gn[K], part[K];
+#pragma unroll
+            for (int n = 0; n < K; ++n) {
+              gn[n] = a.gap_nfp[(size_t)b * K + n];
+              part[n] = 0.f;
+            }
+            for (int c = tid; c < a.C; c += NT) {
+              const float go = a.head_gout[(size_t)b * a.C + c], gxv = a.gap_x[(size_t)b * a.C + c];
+              const float4* wr4 = reinterpret_cast<const float4*>(a.proj_w + (size_t)c * K);
+              float proj = a.proj_b ? a.proj_b[c] : 0.f;
+              const float t = go * gxv;
+#pragma unroll
+              for (int n4 = 0; n4 < K / 4; ++n4) {
+                const float4 w4 = wr4[n4];
+                proj = fmaf(w4.x, gn[4 * n4], proj); proj = fmaf(w4.y, gn[4 * n4 + 1], proj);
+                proj = fmaf(w4.z, gn[4 * n4 + 2], proj); proj = fmaf(w4.w, gn[4 * n4 + 3], proj);
+                part[4 * n4] = fmaf(t, w4.x, part[4 * n4]); part[4 * n4 + 1] = fmaf(t, w4.y, part[4 * n4 + 1]);
+                part[4 * n4 + 2] = fmaf(t, w4.z, part[4 * n4 + 2]); part[4 * n4 + 3] = fmaf(t, w4.w, part[4 * n4 + 3]);
+              }
+              gs[c] = go * proj;
+            }
+#pragma unroll
+            for (int n = 0; n < K; ++n) {
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) part[n] += __shfl_xor_sync(0xffffffffu, part[n], o);
+              if (lane == 0) Gp[warp * K + n] = part[n];   // Gp is free until the stencil loops below
+            }
+            consumer_sync<NT>();
+            if (tid < K) {
+              float sred = 0.f;
+              for (int w = 0; w < NW; ++w) sred += Gp[w * K + tid];
+              reinterpret_cast<float*>(smem_raw + L.gyraw)[tid] = sred * (1.f / (float)P);
+            }
+          }
+        }
+        if (!head_done) {
+          // d GAP(y) / dy: the same value on every pixel of a tap plane
+          if (tid < K) reinterpret_cast<float*>(smem_raw + L.gyraw)[tid] = a.g_gap_nfp[(size_t)b * K + tid] * (1.f / (float)P);
+          if constexpr (MODE == MODE_POOL_BWD) {
+            if (!a.ggx_tma) {  // rows not 16-byte aligned / sized: no bulk copy, stage them with plain loads
+              float* gs = reinterpret_cast<float*>(smem_raw + L.ggx) + (img & 1) * a.C;
+              for (int i = tid; i < a.C; i += NT) gs[i] = a.g_gap_x[(size_t)b * a.C + i];
+            }
           }
         }
         consumer_sync<NT>();
@@ -544,7 +589,27 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
           for (int p = lane; p < P; p += 32) s += ytab[n * P + p];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          if (lane == 0) a.gap_nfp[(size_t)b * K + n] = s / (float)P;
+          if (lane == 0) {
+            a.gap_nfp[(size_t)b * K + n] = s / (float)P;
+            tfull[n] = s / (float)P;   // (the table is dead: every y value has been computed)
+          }
+        }
+        if constexpr (MODE == MODE_POOL_FWD) {
+          if (a.proj_w) {
+            // fused head (NFP_Pooling.py:31-35): out[c] = GAP(x)[c] * (proj_w[c] . GAP(NFP(x)) + proj_b[c])
+            consumer_sync<NT>();   // tfull[0..K) and this CTA's gap_x stores are visible to the whole CTA
+            for (int c = tid; c < a.C; c += NT) {
+              const float4* wr4 = reinterpret_cast<const float4*>(a.proj_w + (size_t)c * K);
+              float proj = a.proj_b ? a.proj_b[c] : 0.f;
+#pragma unroll
+              for (int n4 = 0; n4 < K / 4; ++n4) {
+                const float4 w4 = wr4[n4];
+                proj = fmaf(w4.x, tfull[4 * n4], proj); proj = fmaf(w4.y, tfull[4 * n4 + 1], proj);
+                proj = fmaf(w4.z, tfull[4 * n4 + 2], proj); proj = fmaf(w4.w, tfull[4 * n4 + 3], proj);
+              }
+              a.head_out[(size_t)b * a.C + c] = a.gap_x[(size_t)b * a.C + c] * proj;
+            }
+          }
         }
       }
       NFP_STAMP(2);  // forward outputs written
@@ -936,7 +1001,7 @@ Plan plan_for(const KParams& P) {
   const int max_ctas = want_ctas < 1 ? 1 : (want_ctas > C::MINB ? C::MINB : want_ctas);
   for (int ctas = max_ctas; ctas >= 1 && !pl.ok; --ctas) {
     const int budget = kSmemPerSM / ctas - 2048;  // the runtime reserves 1 KB per CTA; 1 KB slack
-    static const int max_stages = env_int("NFPB200_MAX_STAGES", kMaxStages);
+    static const int max_stages = env_int("NFPB200_MAX_STAGES", 5);  // measured: 4-5 stages beat 6-8 at B = 256
     for (int nst = max_stages < kMaxStages ? max_stages : kMaxStages; nst >= 2; --nst) {  // as many stages as fit
       Smem<T, C, MODE, kNW> L(pl.CC, nst, P.C);
       if (L.total > budget) continue;

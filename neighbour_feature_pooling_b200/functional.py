@@ -283,6 +283,72 @@ class _NFPGapPair(torch.autograd.Function):
         return gx, None, None
 
 
+class _NFPHead(torch.autograd.Function):
+    """out = GAP(x) * (W GAP(NFP(x)) + b) in ONE launch each way (nfpb200_head_forward / _backward); the projection's
+    parameter gradients are three tiny PyTorch ops on the (B, C) / (B, K) tensors the forward leaves behind."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, cfg):
+        desc = _desc_for(x, cfg)
+        B, C = x.shape[:2]
+        w = weight.detach().float().contiguous()
+        bvec = bias.detach().float().contiguous() if bias is not None else None
+        out = torch.empty((B, C), dtype=torch.float32, device=x.device)
+        gap_x = torch.empty((B, C), dtype=torch.float32, device=x.device)
+        gap_nfp = torch.empty((B, cfg.out_channels), dtype=torch.float32, device=x.device)
+        if PATH_TRACE is not None:
+            PATH_TRACE.add(f"{_capi.describe_path(desc, _capi.OP_POOL_FORWARD)} "
+                           f"{'bf16' if desc.dtype == _capi.BF16 else 'f32'} nchw fused head (GAP, GAP(NFP), proj, product)")
+        with torch.cuda.device(x.device):
+            rc = _capi.load().nfpb200_head_forward(ctypes.byref(desc), x.data_ptr(), w.data_ptr(),
+                                                   bvec.data_ptr() if bvec is not None else None, out.data_ptr(),
+                                                   gap_x.data_ptr(), gap_nfp.data_ptr(), _stream(x.device))
+        _capi.check(rc, "nfpb200_head_forward")
+        ctx.save_for_backward(x, w, bvec if bvec is not None else w.new_empty(0), gap_x, gap_nfp)
+        ctx.cfg = cfg
+        ctx.has_bias = bias is not None
+        ctx.param_dtypes = (weight.dtype, bias.dtype if bias is not None else None)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_out):
+        x, w, bvec, gap_x, gap_nfp = ctx.saved_tensors
+        desc = _desc_for(x, ctx.cfg)
+        if _X_STABLE_HINT:
+            desc.path |= _capi.HINT_X_STABLE
+        g_out = g_out.float().contiguous()
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            rc = _capi.load().nfpb200_head_backward(ctypes.byref(desc), x.data_ptr(), w.data_ptr(),
+                                                    bvec.data_ptr() if ctx.has_bias else None, gap_x.data_ptr(),
+                                                    gap_nfp.data_ptr(), g_out.data_ptr(), gx.data_ptr(),
+                                                    _stream(x.device))
+        _capi.check(rc, "nfpb200_head_backward")
+        t = g_out * gap_x                                   # d loss / d proj  (B, C)
+        gw = (t.t() @ gap_nfp).to(ctx.param_dtypes[0]) if ctx.needs_input_grad[1] else None
+        gb = t.sum(0).to(ctx.param_dtypes[1]) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb, None
+
+
+def nfp_head(x: torch.Tensor, weight: torch.Tensor, bias, cfg: NFPConfig):
+    """``GAP(x) * (weight @ GAP(NFP(x)) + bias)`` -> (B, C): the whole nfp_pooling head (NFP_Pooling.py:25-36) fused
+    into the pooled kernels.  Returns None when the problem is not covered (the caller composes the pieces)."""
+    if x.device.type != "cuda" or x.dim() != 4 or weight.device != x.device:
+        return None
+    _check_geometry(x.shape[2], x.shape[3], cfg)
+    xk, out_dtype, layout = _prepare(x, cfg)
+    if layout != _capi.LAYOUT_NCHW:
+        return None
+    desc = _desc_for(xk, cfg)
+    if _capi.load().nfpb200_head_supported(ctypes.byref(desc)) != 0:
+        return None
+    out = _NFPHead.apply(xk, weight, bias, cfg)
+    # NFP_Pooling.py:35: x_avg (dtype of x) * nfp_proj(...) (autocast dtype under autocast, else the parameter dtype)
+    proj_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else weight.dtype
+    return out.to(torch.promote_types(x.dtype, proj_dtype))
+
+
 def nfp_similarity(x: torch.Tensor, cfg: NFPConfig) -> torch.Tensor:
     """(B, C, H, W) -> (B, k*k-1, H', W') similarity map; differentiable w.r.t. ``x``."""
     if x.device.type != "cuda":
@@ -317,5 +383,5 @@ def describe(x_shape, dtype: torch.dtype, cfg: NFPConfig, op: int = _capi.OP_FOR
     return _capi.describe_path(desc, op)
 
 
-__all__ = ["NFPConfig", "nfp_similarity", "nfp_gap_pair", "shape_probe", "conv_output_size", "describe",
+__all__ = ["NFPConfig", "nfp_similarity", "nfp_gap_pair", "nfp_head", "shape_probe", "conv_output_size", "describe",
            "replace", "math"]

@@ -193,6 +193,12 @@ class nfp_pooling(nn.Module):
     def forward(self, x):
         layer = self.nfp_layer
         if x.device.type == "cuda" and self._fusable():
+            if (type(self.nfp_proj) is nn.Linear and not self.nfp_proj._forward_hooks
+                    and not self.nfp_proj._forward_pre_hooks):
+                # the whole head in one launch each way: GAP(x), GAP(NFP(x)), the K -> C projection and the product
+                out = NF.nfp_head(x, self.nfp_proj.weight, self.nfp_proj.bias, layer.config)
+                if out is not None:
+                    return out
             x_avg, x_nfp = NF.nfp_gap_pair(x, layer.config)
         else:
             # foreign / customised nfp_layer module, or a CPU shape probe (NFPPooling answers those itself)

@@ -673,3 +673,63 @@ def test_fp32_tokens_under_autocast_take_the_token_kernels(cuda_device):
     y_ref, gx_ref = O.nfp_forward_backward(xq, g.double(), R=1, measure="cosine", padding=1)
     assert rel_err(y.detach().cpu(), y_ref) < 1e-5
     assert rel_err(fd.grad[:, 1:].transpose(1, 2).reshape(B, C, H, W).cpu(), gx_ref) < BF16_TOL
+
+
+@pytest.mark.parametrize("shape", [(5, 64, 7, 7, 1), (3, 512, 7, 7, 1), (2, 960, 7, 7, 1), (3, 256, 14, 14, 1),
+                                   (6, 512, 2, 2, 1), (3, 128, 7, 7, 2), (300, 16, 7, 7, 1)],
+                         ids=lambda s: "x".join(map(str, s[:4])) + f"_r{s[4]}")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_fused_head_matches_composition_and_oracle(shape, dtype, cuda_device):
+    """the whole nfp_pooling head (NFP_Pooling.py:25-36) -- GAP(x), GAP(NFP(x)), the K -> C projection and
+    the product -- is one launch each way (nfpb200_head_forward / _backward).  Output and all three gradients (x,
+    nfp_proj.weight, nfp_proj.bias) against the oracle and against the unfused composition."""
+    B, C, H, W, R = shape
+    K = (2 * R + 1) ** 2 - 1
+    gen = torch.Generator().manual_seed(B + 3 * C + H)
+    x = torch.randn(B, C, H, W, generator=gen)
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    g = torch.randn(B, C, generator=gen)
+    params = {"num_ftrs": {"m": C}, "Model_name": "m", "Dataset": "d", "num_classes": {"d": 3}}
+    layer = NFPPooling(C, R=R, measure="cosine", padding=R)
+    torch.manual_seed(7)
+    head = nfp_pooling(nfp_layer=layer, Params=params).to(cuda_device)
+    Wp, bp = head.nfp_proj.weight.detach().cpu().double(), head.nfp_proj.bias.detach().cpu().double()
+    # oracle: fp64 autograd through the gather-form similarity map
+    xr = x.double()
+    gy_unit = torch.zeros(B, K, H, W, dtype=torch.float64)
+    y_map = torch.as_tensor(np.asarray(O.nfp_forward(xr, R=R, measure="cosine", padding=R)))
+    gap_n = y_map.mean((2, 3))
+    gap_x = xr.mean((2, 3))
+    proj = gap_n @ Wp.t() + bp
+    out_ref = gap_x * proj
+    t = g.double() * gap_x
+    gW_ref, gb_ref = t.t() @ gap_n, t.sum(0)
+    g_gap_n = t @ Wp
+    gy = (g_gap_n / (H * W))[:, :, None, None].expand(B, K, H, W).contiguous()
+    _, gx_map = O.nfp_forward_backward(xr, gy, R=R, measure="cosine", padding=R)
+    gx_ref = torch.as_tensor(np.asarray(gx_map)) + ((g.double() * proj) / (H * W))[:, :, None, None]
+    xd = x.to(cuda_device, dtype).requires_grad_(True)
+    NF.PATH_TRACE = set()
+    try:
+        out = head(xd)
+    finally:
+        paths, NF.PATH_TRACE = NF.PATH_TRACE, None
+    assert any("fused head" in p for p in paths), paths
+    out.backward(g.to(cuda_device, out.dtype))
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert rel_err(out.detach().float().cpu(), out_ref) < tol
+    assert rel_err(xd.grad.float().cpu(), gx_ref) < tol
+    assert rel_err(head.nfp_proj.weight.grad.cpu(), gW_ref) < tol
+    assert rel_err(head.nfp_proj.bias.grad.cpu(), gb_ref) < tol
+    if dtype != torch.float32:
+        return   # (bf16 x with fp32 projection parameters is a dtype error in the unfused composition, as in the reference)
+    # the unfused composition (forward hook on the projection switches the fused head off) agrees
+    head.zero_grad()
+    h = head.nfp_proj.register_forward_hook(lambda m, i, o: None)
+    x2 = x.to(cuda_device, dtype).requires_grad_(True)
+    out2 = head(x2)
+    h.remove()
+    out2.backward(g.to(cuda_device, out2.dtype))
+    assert rel_err(out2.detach().float().cpu(), out.detach().float().cpu()) < (1e-5 if dtype == torch.float32 else 2e-2)
+    assert rel_err(x2.grad.float().cpu(), xd.grad.float().cpu()) < (1e-5 if dtype == torch.float32 else 2e-2)
