@@ -392,7 +392,38 @@ def e2e_through_module(dev, B, C, H, W, R, dtype_name, steps, warmup, sampler, b
     esz = 4 if dtype_name == "fp32" else 2
     h2d = (B * C * H * W + B * K * H * W) * esz
     d2h = h2d
-    return e0.elapsed_time(e1) * 1e-3, h2d, d2h, float(hy[0].float().abs().sum())
+    t_e2e = e0.elapsed_time(e1) * 1e-3
+    # the host-link ceiling of this step: the same pinned buffers copied in and out concurrently, no kernels, every rank
+    # at once (all ranks share the host's memory / PCIe fabric, so the per-rank rate drops as ranks are added)
+    dy_ = [torch.empty(B, K, H, W, dtype=tdtype, device=dev) for _ in range(nd)]
+    dgx_ = [torch.empty(B, C, H, W, dtype=tdtype, device=dev) for _ in range(nd)]
+
+    def copies(i):
+        j, h = i % nd, i % nh
+        with torch.cuda.stream(s_in):
+            dx[j].copy_(hx[h], non_blocking=True)
+            dg[j].copy_(hg[h], non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hy[h].copy_(dy_[j], non_blocking=True)
+            hgx[h].copy_(dgx_[j], non_blocking=True)
+    for i in range(3):
+        copies(i)
+    torch.cuda.synchronize(dev)
+    if barrier:
+        barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for st in (s_in, s_out):
+        st.wait_event(c0)
+    for i in range(steps):
+        copies(i)
+    drain()
+    c1.record()
+    c1.synchronize()
+    t_link = c0.elapsed_time(c1) * 1e-3
+    link = {"seconds_per_step_copies_only": t_link / steps, "h2d_gbs_per_rank": h2d * steps / t_link / 1e9,
+            "d2h_gbs_per_rank": d2h * steps / t_link / 1e9}
+    return t_e2e, h2d, d2h, link
 
 
 # ----------------------------------------------------------------------------------------------
@@ -600,10 +631,15 @@ def main():
     t_bwd_hint = lb.timed(lb.bwd, n_cons, 5, sampler, "kernels", windows=3) / n_cons
     # ---- e2e through the nn.Module API with host buffers ------------------------------------------------
     e2e_steps = min(args.steps, 50)
-    t_e2e, h2d, d2h, _chk = e2e_through_module(dev, B, C, H, W, R, args.dtype, e2e_steps, min(args.warmup, 5),
+    t_e2e, h2d, d2h, link = e2e_through_module(dev, B, C, H, W, R, args.dtype, e2e_steps, min(args.warmup, 5),
                                                sampler, barrier)
     t_e2e = max_over_ranks(t_e2e)
     e2e_value = world * e2e_steps * B / t_e2e
+    t_link = max_over_ranks(link["seconds_per_step_copies_only"])
+    link["ceiling_maps_per_s"] = world * B / t_link      # what the host link alone allows at this rank count
+    link["e2e_fraction_of_ceiling"] = e2e_value / link["ceiling_maps_per_s"]
+    link["note"] = ("copies only (same pinned buffers, both directions at once, all ranks concurrently): the e2e number "
+                    "is bound by this, not by the kernels; pinned memory is not NUMA-bound per rank")
 
     # ---- pooled mode: the nfp_pooling head path, same shape, device resident -----------------
     lb.pool_setup()
@@ -698,7 +734,7 @@ def main():
                                  "backward: no NFPB200_HINT_X_STABLE -- see with_x_stable_hint for the hinted order)",
                        "kernel_path": {"forward": lb.path_fwd, "backward": lb.path_bwd}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": t_e2e / e2e_steps * 1e3,
+                    "steps": e2e_steps, "ms_per_step": t_e2e / e2e_steps * 1e3, "host_link": link,
                     "api": "NFPPooling(C,R,'cosine',padding=R).forward + autograd backward; pinned host x, grad_y -> "
                            "device; y, grad_x -> pinned host, every step; copy-in / kernels / copy-out on three "
                            "streams over three device buffer sets (pipelined, PCIe full duplex)"},
