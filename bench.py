@@ -223,6 +223,10 @@ class LayerBench:
         self.fwd(i)
         self.bwd_conservative(self.cold(i))
 
+    def step_r1(self, i):             # round 1's definition: hinted backward on the buffers its forward has just read
+        self.fwd(i)
+        self.bwd(i)
+
     def step_hinted(self, i):         # backward with NFPB200_HINT_X_STABLE, as the autograd function passes it
         self.fwd(i)
         self.bwd(self.cold(i))
@@ -629,6 +633,7 @@ def main():
     n_cons = max(min(args.steps, 300), 100)
     t_step_hint = lb.timed(lb.step_hinted, n_cons, 5, sampler, "kernels", windows=3) / n_cons
     t_bwd_hint = lb.timed(lb.bwd, n_cons, 5, sampler, "kernels", windows=3) / n_cons
+    t_step_r1 = lb.timed(lb.step_r1, n_cons, 5, sampler, "kernels", windows=3) / n_cons
     # ---- e2e through the nn.Module API with host buffers ------------------------------------------------
     e2e_steps = min(args.steps, 50)
     t_e2e, h2d, d2h, link = e2e_through_module(dev, B, C, H, W, R, args.dtype, e2e_steps, min(args.warmup, 5),
@@ -753,6 +758,9 @@ def main():
                                    "maps_per_s": world * B / t_step_hint,
                                    "step_frac": (fwd_bytes + bwd_bytes) / t_step_hint / 1e9 / hbm_peak,
                                    "bwd_frac": bwd_bytes / t_bwd_hint / 1e9 / hbm_peak,
+                                   "us_per_step_round1_definition": t_step_r1 * 1e6,
+                                   "round1_definition": "hinted backward on the buffer set its forward has just read (x L2-warm): "
+                                                        "what BENCH_r01's `value` measured; kept for round-over-round comparison",
                                    "note": "NFPB200_HINT_X_STABLE (include/nfp_b200.h; what the autograd function passes: "
                                            "x is a saved activation) lets a fused backward stream x while the preceding "
                                            "launch drains; it only pays when NFP launches are adjacent on the stream, as "

@@ -154,6 +154,7 @@ def run_gpu(config="eurosat", batch=256, steps=20, warmup=5, amp=True, use_graph
     replayed; if capture fails the eager step is timed instead and the reason is reported."""
     import torch.distributed as dist
     cfg = CONFIGS[config]
+    loss_scale = 1.0
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -175,6 +176,14 @@ def run_gpu(config="eurosat", batch=256, steps=20, warmup=5, amp=True, use_graph
             if os.environ.get("NFP_DDP_BF16_HOOK", "0") == "1":
                 from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
                 model.register_comm_hook(None, default_hooks.bf16_compress_hook)
+            elif os.environ.get("NFP_DDP_SUM_HOOK", "0") == "1":
+                # DDP's default path divides every parameter's gradient by the world size with its own small kernel
+                # (56 launches, 155 us per step at N = 8: profiles/r02_train_timeline_n8.txt).  A SUM all-reduce of the
+                # bucket with the 1/world factor folded into the loss is the same average with no extra kernel.
+                def sum_hook(state, bucket):
+                    return dist.all_reduce(bucket.buffer(), async_op=True).get_future().then(lambda f: f.value()[0])
+                model.register_comm_hook(None, sum_hook)
+                loss_scale = 1.0 / world
         opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4, capturable=use_graph)
     crit = nn.CrossEntropyLoss(label_smoothing=0.05)
     gen = torch.Generator().manual_seed(100 + rank)
@@ -208,7 +217,7 @@ def run_gpu(config="eurosat", batch=256, steps=20, warmup=5, amp=True, use_graph
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
             loss = crit(model(x).float(), y)
         opt.zero_grad(set_to_none=True)
-        loss.backward()
+        (loss * loss_scale if loss_scale != 1.0 else loss).backward()
         opt.step()
         return loss
 
