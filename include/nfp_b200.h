@@ -82,7 +82,10 @@ enum {
 enum {
   NFPB200_PATH_AUTO = 0,    /* fused kernels when the problem qualifies, else the planar, else the generic kernels */
   NFPB200_PATH_GENERIC = 1, /* force the geometry-/measure-generic kernels */
-  NFPB200_PATH_FUSED = 2    /* force the fused kernels; NFPB200_EUNSUPPORTED when the problem does not qualify */
+  NFPB200_PATH_FUSED = 2,   /* force the fused kernels; NFPB200_EUNSUPPORTED when the problem does not qualify */
+  NFPB200_PATH_SPLIT = 3    /* the cluster-split fused kernels (one thread-block cluster per image, DSMEM table exchange):
+                               a measured experiment kept selectable for A/B runs and tests; same results, slower at B = 256.
+                               NFPB200_EUNSUPPORTED when the problem does not qualify */
 };
 
 /* Optional hint, OR-ed into nfpb200_desc_t.path, for nfpb200_backward / nfpb200_pool_backward: `x` was NOT written by

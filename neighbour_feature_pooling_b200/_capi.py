@@ -25,7 +25,7 @@ MEASURES = {
     "pearson": 12, "jeffrey": 13, "squaredchord": 14, "smith": 15, "scs": 16,
     "sharpened_cosine": 16,  # nfp.py:117 accepts both spellings
 }
-PATHS = {"auto": 0, "generic": 1, "fused": 2}
+PATHS = {"auto": 0, "generic": 1, "fused": 2, "split": 3}
 HINT_X_STABLE = 0x100   # NFPB200_HINT_X_STABLE, OR-ed into Desc.path for the backward entry points
 FLAG_Y_F32 = 0x200      # NFPB200_FLAG_Y_F32, OR-ed into Desc.path for nfpb200_forward with bf16 x: y is fp32
 OP_FORWARD, OP_BACKWARD, OP_POOL_FORWARD, OP_POOL_BACKWARD = 0, 1, 2, 3

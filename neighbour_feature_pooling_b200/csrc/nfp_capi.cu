@@ -21,7 +21,7 @@ int make_params(const nfpb200_desc_t* d, KParams* out) {
   if (d->R < 1 || d->stride < 1 || d->dilation < 1 || d->padding < 0) return NFPB200_EINVAL;
   if (d->padding_mode < NFPB200_PAD_ZEROS || d->padding_mode > NFPB200_PAD_CIRCULAR) return NFPB200_EINVAL;
   if (d->measure < 0 || d->measure >= NFPB200_NUM_MEASURES) return NFPB200_EINVAL;
-  if ((d->path & ~kPathFlags) < NFPB200_PATH_AUTO || (d->path & ~kPathFlags) > NFPB200_PATH_FUSED) return NFPB200_EINVAL;
+  if ((d->path & ~kPathFlags) < NFPB200_PATH_AUTO || (d->path & ~kPathFlags) > NFPB200_PATH_SPLIT) return NFPB200_EINVAL;
   KParams P{};
   P.B = d->B; P.C = d->C; P.H = d->H; P.W = d->W;
   P.R = d->R; P.k = 2 * d->R + 1; P.K = P.k * P.k - 1;
@@ -46,6 +46,7 @@ int make_params(const nfpb200_desc_t* d, KParams* out) {
   }
   P.similarity = d->similarity != 0;
   P.x_stable = (d->path & NFPB200_HINT_X_STABLE) != 0;
+  P.force_split = (d->path & ~kPathFlags) == NFPB200_PATH_SPLIT;
   P.y_f32 = (d->path & NFPB200_FLAG_Y_F32) != 0 && d->dtype == NFPB200_BF16;
   P.diff_taps = d->difference_taps != 0;
   P.eps = d->eps; P.p = d->p; P.q = d->q_scs;
@@ -69,7 +70,7 @@ int choose_path(const nfpb200_desc_t* d, const KParams& P, int op) {
   }
   const int fused = stream_supported(P, d->dtype, d->measure, op) ? 2 : 0;
   const int want = d->path & ~kPathFlags;
-  if (want == NFPB200_PATH_FUSED) return fused ? fused : NFPB200_EUNSUPPORTED;
+  if (want == NFPB200_PATH_FUSED || want == NFPB200_PATH_SPLIT) return fused ? fused : NFPB200_EUNSUPPORTED;
   if (want == NFPB200_PATH_GENERIC) return 0;
   if (fused) return fused;
   // large or odd-sized maps (the multi-stage heads' 112x112 ... 28x28 maps): per-pixel planar kernels

@@ -22,6 +22,7 @@ struct KParams {
   int similarity, diff_taps, pkind;
   int layout;           // NFPB200_LAYOUT_*
   long long x_batch_stride, gx_batch_stride;  // NHWC: elements between images (0 = dense)
+  int force_split;      // NFPB200_PATH_SPLIT: the cluster-split kernels or nothing
   int y_f32;            // NFPB200_FLAG_Y_F32: forward writes y as fp32 although x is bf16
   int x_stable;         // NFPB200_HINT_X_STABLE: x is not an output of the launch that precedes this one
   float eps, p, q;

@@ -33,7 +33,7 @@ bool split_ok(const KParams& P, int dtype, int mode) {
     const char* e = getenv("NFPB200_FUSED_IMPL");
     return e && strcmp(e, "split") == 0;
   }();
-  if (!want_split) return false;
+  if (!want_split && !P.force_split) return false;
   return (dtype == NFPB200_BF16 ? split::plan_bf16(P, mode) : split::plan_f32(P, mode)).ok;
 }
 
@@ -61,6 +61,7 @@ int run(const KParams& P, int dtype, int mode, stream::StreamArgs a, cudaStream_
 bool stream_supported(const KParams& P, int dtype, int measure, int op) {
   if (!geometry_ok(P, measure)) return false;
   if (split_ok(P, dtype, op_mode(op))) return true;
+  if (P.force_split) return false;
   return dtype == NFPB200_BF16 ? stream::plan_ok_bf16(P, op_mode(op)) : stream::plan_ok_f32(P, op_mode(op));
 }
 

@@ -177,6 +177,14 @@ def test_fused_cosine_vs_oracle(shape, mode, dtype, cuda_device):
         # and the CUDA paths agree with each other
         y2, gx2 = _run(x, g, kw, cuda_device, path="generic")
         assert rel_err(y, y2) < FP32_TOL and rel_err(gx, gx2) < FP32_TOL
+    # the cluster-split kernels (NFPB200_PATH_SPLIT: the measured experiment of DESIGN.md 4.2) on the same problem
+    cfg_split = NF.replace(cfg, path="split")
+    assert NF.describe(shape[:4], dtype, cfg_split).startswith("fused/split")
+    y3, gx3 = _run(x, g, kw, cuda_device, dtype=dtype, path="split")
+    if B > 32:
+        y3, gx3 = y3[sl], gx3[sl]
+    assert rel_err(y3, y_ref) < tol
+    assert rel_err(gx3, gx_ref) < tol
 
 
 @pytest.mark.parametrize("shape", [(40, 8, 7, 7, 1), (40, 16, 7, 7, 2), (24, 2, 14, 14, 1), (24, 4, 14, 14, 2),
@@ -535,6 +543,14 @@ def test_pooled_vs_oracle(case, dtype, cuda_device):
     assert rel_err(a.detach().float().cpu(), gap_x_ref) < tol
     assert rel_err(n.detach().float().cpu(), gap_nfp_ref) < tol
     assert rel_err(xd.grad.float().cpu(), gx_ref) < tol
+    if NF.describe((B, C, H, W), dtype, cfg, op=2).startswith("fused/"):   # the cluster-split pooled kernels as well
+        cfg_s = NF.replace(cfg, path="split")
+        xs_ = x.to(cuda_device, dtype).requires_grad_(True)
+        a2, n2 = NF.nfp_gap_pair(xs_, cfg_s)
+        ((a2.float() * g1.to(cuda_device)).sum() + (n2.float() * g2.to(cuda_device)).sum()).backward()
+        assert rel_err(a2.detach().float().cpu(), gap_x_ref) < tol
+        assert rel_err(n2.detach().float().cpu(), gap_nfp_ref) < tol
+        assert rel_err(xs_.grad.float().cpu(), gx_ref) < tol
 
 
 def test_nfp_pooling_respects_customised_layers(cuda_device):
