@@ -66,7 +66,9 @@ struct TokenArgs {
 
 #define NFP_TSTAMP(k) do { if (a.dbg && tid == 0 && it < 2) a.dbg[((size_t)blockIdx.x * 2 + it) * 8 + (k)] = globaltimer_ns(); } while (0)
 
-constexpr int kNW = 16, kNT = kNW * 32;   // 4 warps per SM sub-partition: the MMA / ldmatrix latencies overlap across warps
+// warps per CTA: 16 with one CTA per SM (two image buffers), or 8 with two CTAs per SM (one buffer each) when both fit:
+// the scalar table / coefficient phases of one image then overlap the tensor-core phases of the other
+constexpr int kNWBig = 16, kNWSmall = 8;
 constexpr int kSmemPerSM = 227 * 1024;
 constexpr int kMaxKS = 8;
 constexpr int kStgStride = 144;  // bytes per staged gx row: 64 channels + 16 (conflict-free fragment stores)
@@ -107,7 +109,7 @@ struct Geo {
 };
 
 // Shared-memory layout (byte offsets)
-template <class C, int MODE>
+template <class C, int MODE, int NW>
 struct Lay {
   static constexpr bool BWD = (MODE == MODE_BWD || MODE == MODE_POOL_BWD);
   int tfull, tpart, inv, rn, wd, gp, tabs, gyraw, ggx, mhi, mlo, stg, ytab, eidx, xs, total;
@@ -128,7 +130,7 @@ struct Lay {
     gp = take(BWD ? C::P * C::KK * 4 : 0);
     const int u1 = o;
     o = u0;
-    stg = take(BWD ? kNW * 16 * kStgStride : 0);
+    stg = take(BWD ? NW * 16 * kStgStride : 0);
     if (o < u1) o = u1;
     tabs = take(BWD ? Tables<C>::BWD_BYTES : Tables<C>::FWD_BYTES);
     if (BWD) {
@@ -156,19 +158,19 @@ struct Lay {
   }
 };
 
-template <class C, int MODE>
-__global__ void __launch_bounds__(kNT, 1) token_kernel(const TokenArgs a, const Tables<C>* __restrict__ gt) {
+template <class C, int MODE, int NW>
+__global__ void __launch_bounds__(NW * 32, NW == kNWSmall ? 2 : 1) token_kernel(const TokenArgs a, const Tables<C>* __restrict__ gt) {
   using G = Geo<C>;
   constexpr int W = C::W, R = C::R, k = C::k, KK = C::KK, K = C::K, P = C::P, NV = C::NV, PNV = C::PNV;
   constexpr int PPAD = G::PPAD, MT = G::MT, NTN = G::NTN, HT = G::HT, KTN = G::KTN, MS = G::MS;
   constexpr bool BWD = (MODE == MODE_BWD || MODE == MODE_POOL_BWD);
   constexpr bool POOLED = (MODE == MODE_POOL_FWD || MODE == MODE_POOL_BWD);
-  constexpr int NT = kNT, NW = kNW;
+  constexpr int NT = NW * 32;
   constexpr int GY_BYTES = K * P * 2;
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int Cch = a.C, NBUF = a.nbuf, KS = a.KS;
-  const Lay<C, MODE> L(Cch, NBUF, KS);
+  const Lay<C, MODE, NW> L(Cch, NBUF, KS);
   float* tfull = reinterpret_cast<float*>(smem_raw + L.tfull);
   float* tpart = reinterpret_cast<float*>(smem_raw + L.tpart);
   float* inv = reinterpret_cast<float*>(smem_raw + L.inv);
@@ -547,38 +549,47 @@ __global__ void __launch_bounds__(kNT, 1) token_kernel(const TokenArgs a, const 
 
 struct Plan {
   bool ok;
-  int nbuf, KS;
+  int nbuf, KS, nw, ctas;
   size_t smem;
 };
 
-template <class C, int MODE>
-Plan plan_for(const KParams& P) {
-  Plan pl{false, 0, 0, 0};
+template <class C, int MODE, int NW>
+bool plan_try(const KParams& P, int nbuf, int budget, Plan& pl) {
   using G = Geo<C>;
-  if (P.C % 64 || P.C < 64) return pl;             // swizzle granule: 8 chunks of 8 channels
-  if ((C::K * C::P * 2) % 16) return pl;           // upstream-gradient rows are fetched with 16-byte copies
   int ks = 1;
-  while (ks < kMaxKS && ks * G::MT < kNW && P.C % (2 * ks) == 0 && (P.C / (2 * ks)) % 16 == 0) ks *= 2;
+  while (ks < kMaxKS && ks * G::MT < NW && P.C % (2 * ks) == 0 && (P.C / (2 * ks)) % 16 == 0) ks *= 2;
+  Lay<C, MODE, NW> L(P.C, nbuf, ks);
+  if (L.total > budget) return false;
+  pl.ok = true;
+  pl.nbuf = nbuf;
   pl.KS = ks;
-  for (int nbuf = 2; nbuf >= 1 && !pl.ok; --nbuf) {
-    Lay<C, MODE> L(P.C, nbuf, ks);
-    if (L.total > kSmemPerSM - 1024) continue;
-    pl.ok = true;
-    pl.nbuf = nbuf;
-    pl.smem = (size_t)L.total;
-  }
-  return pl;
+  pl.nw = NW;
+  pl.smem = (size_t)L.total;
+  return true;
 }
 
 template <class C, int MODE>
-int launch_mode(const KParams& P, TokenArgs a, cudaStream_t stream) {
-  const Plan pl = plan_for<C, MODE>(P);
-  if (!pl.ok) return NFPB200_EUNSUPPORTED;
+Plan plan_for(const KParams& P) {
+  Plan pl{false, 0, 0, 0, 0, 0};
+  if (P.C % 64 || P.C < 64) return pl;             // swizzle granule: 8 chunks of 8 channels
+  if ((C::K * C::P * 2) % 16) return pl;           // upstream-gradient rows are fetched with 16-byte copies
+  static const int want_two = [] { const char* e = getenv("NFPB200_TOKEN_TWO_CTAS"); return e ? atoi(e) : 1; }();
+  // two 8-warp CTAs per SM (one image buffer each) when they fit and there is more than one image per SM to overlap
+  if (want_two && plan_try<C, MODE, kNWSmall>(P, 1, kSmemPerSM / 2 - 1024, pl)) {
+    pl.ctas = 2;
+    return pl;
+  }
+  if (plan_try<C, MODE, kNWBig>(P, 2, kSmemPerSM - 1024, pl) || plan_try<C, MODE, kNWBig>(P, 1, kSmemPerSM - 1024, pl)) pl.ctas = 1;
+  return pl;
+}
+
+template <class C, int MODE, int NW>
+int launch_nw(const KParams& P, const Plan& pl, TokenArgs a, cudaStream_t stream) {
   a.nbuf = pl.nbuf;
   a.KS = pl.KS;
   a.KSlog = 0;
   while ((1 << a.KSlog) < pl.KS) ++a.KSlog;
-  auto kern = token_kernel<C, MODE>;
+  auto kern = token_kernel<C, MODE, NW>;
   constexpr int kMaxDev = 64;
   static int sm_count[kMaxDev] = {0};
   int dev = 0;
@@ -595,10 +606,11 @@ int launch_mode(const KParams& P, TokenArgs a, cudaStream_t stream) {
   }
   const Tables<C>* gt = tables_for<C>(a.pad_mode);
   if (!gt) return NFPB200_EINVAL;
-  const int grid = P.B < sm_count[dev] ? P.B : sm_count[dev];
+  const int slots = sm_count[dev] * pl.ctas;
+  const int grid = P.B < slots ? P.B : slots;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kNT);
+  cfg.blockDim = dim3(NW * 32);
   cfg.dynamicSmemBytes = pl.smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -607,6 +619,13 @@ int launch_mode(const KParams& P, TokenArgs a, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return (int)cudaLaunchKernelEx(&cfg, kern, a, gt);
+}
+
+template <class C, int MODE>
+int launch_mode(const KParams& P, TokenArgs a, cudaStream_t stream) {
+  const Plan pl = plan_for<C, MODE>(P);
+  if (!pl.ok) return NFPB200_EUNSUPPORTED;
+  return pl.nw == kNWSmall ? launch_nw<C, MODE, kNWSmall>(P, pl, a, stream) : launch_nw<C, MODE, kNWBig>(P, pl, a, stream);
 }
 
 template <class C>
