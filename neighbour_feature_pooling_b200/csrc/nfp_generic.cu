@@ -4,11 +4,11 @@
 // (models/pooling/nfp.py:16-18): any radius, stride, padding, dilation, padding mode and all 17
 // measures, forward and backward.  They read x straight from global memory (L1/L2 provide the
 // reuse) with one thread per (centre, neighbour) pair, so they are correct everywhere but not
-// tuned; the hot configurations are taken by the fused slab kernels in nfp_fused.cu.
+// tuned; the hot configurations are taken by the fused kernels (nfp_stream_impl.cuh, nfp_token.cu).
 //
 // Forward:   pair kernel -> y                                   (+ a second pass for attention / scs)
 // Backward:  pair kernel -> 5 coefficients per pair (workspace) (+ a second pass for attention / scs)
-//            init gx32, scatter kernel (fp32 atomics), convert to bf16 when needed.
+//            gather kernel (inverse index map, fixed order, no atomics) writes gx in its own dtype.
 #include "nfp_common.cuh"
 
 namespace nfp {
@@ -452,60 +452,94 @@ __global__ void __launch_bounds__(kThreads) scs_coef_kernel_b(float* __restrict_
   coef[2 * npairs + idx] = nn > 0.f ? gden * (nc + P.q) / nn : 0.f;
 }
 
-// gx32 = g_gap_x / (H*W) broadcast over the plane (pooled mode) or 0
-__global__ void __launch_bounds__(kThreads) init_grad_kernel(float* __restrict__ gx32,
-                                                             const float* __restrict__ g_gap_x, int HW,
-                                                             long long total) {
-  long long idx = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (idx >= total) return;
-  gx32[idx] = g_gap_x ? g_gap_x[idx / HW] / (float)HW : 0.f;
+// Every padded coordinate p (frame: i*stride + a*dil - pad) that the padding rule maps onto source coordinate r.
+template <class F>
+__device__ __forceinline__ void for_each_preimage(int r, int n, int pad, int mode, F f) {
+  f(r);
+  switch (mode) {
+    case NFPB200_PAD_REFLECT:
+      if (r >= 1 && r <= pad) f(-r);
+      if (r <= n - 2 && n - 1 - r <= pad) f(2 * (n - 1) - r);
+      break;
+    case NFPB200_PAD_REPLICATE:
+      if (r == 0) for (int p = -pad; p < 0; ++p) f(p);
+      if (r == n - 1) for (int p = n; p < n + pad; ++p) f(p);
+      break;
+    case NFPB200_PAD_CIRCULAR:
+      if (r - n >= -pad) f(r - n);
+      if (r + n <= n - 1 + pad) f(r + n);
+      break;
+    default: break;
+  }
 }
 
-// One thread per (b, channel, output pixel): walks the K taps, accumulates the centre gradient in
-// a register and scatters the neighbour gradients with fp32 atomics.
+// Gather form of the backward: one thread per (b, channel, INPUT pixel q) collects, in a fixed order, every
+// contribution that lands on q -- as a neighbour tap of an output pixel (d/dn) and as the centre of an output pixel
+// (sum over its taps of d/dc) -- through the inverse of the padding / stride / dilation index map.  No atomics:
+// bit-reproducible for every measure and geometry; gx is written once, in its own dtype.
 template <typename T, int M>
-__global__ void __launch_bounds__(kThreads) scatter_kernel(const T* __restrict__ x, const float* __restrict__ coef,
-                                                           float* __restrict__ gx32, KParams P,
-                                                           long long npairs, long long total) {
+__global__ void __launch_bounds__(kThreads) gather_kernel(const T* __restrict__ x, const float* __restrict__ coef,
+                                                          T* __restrict__ gx, const float* __restrict__ g_gap_x,
+                                                          KParams P, long long npairs, long long total) {
   long long idx = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (idx >= total) return;
-  const int j = (int)(idx % P.Wo);
-  long long r = idx / P.Wo;
-  const int i = (int)(r % P.Ho);
-  r /= P.Ho;
+  const int w = (int)(idx % P.W);
+  long long r = idx / P.W;
+  const int h = (int)(r % P.H);
+  r /= P.H;
   const int ch = (int)(r % P.C);
   const int b = (int)(r / P.C);
   const int HW = P.H * P.W;
   const size_t plane = ((size_t)b * P.C + ch) * HW;
-  const int rc = map_index(i * P.stride + P.R * P.dil - P.pad, P.H, P.mode);
-  const int cc = map_index(j * P.stride + P.R * P.dil - P.pad, P.W, P.mode);
-  const bool cvalid = rc >= 0 && cc >= 0;
-  const float c = cvalid ? to_f32(x[plane + rc * P.W + cc]) : 0.f;
-  float dc_sum = 0.f;
   const long long HoWo = (long long)P.Ho * P.Wo;
-  const long long pbase = (long long)b * P.K * HoWo + (long long)i * P.Wo + j;
-  for (int t = 0; t < P.K; ++t) {
-    int a, bb;
-    tap_rc(t, P.k, P.K, a, bb);
-    const int rn = map_index(i * P.stride + a * P.dil - P.pad, P.H, P.mode);
-    const int cn = map_index(j * P.stride + bb * P.dil - P.pad, P.W, P.mode);
-    const bool nvalid = rn >= 0 && cn >= 0;
-    const float n = nvalid ? to_f32(x[plane + rn * P.W + cn]) : 0.f;
-    float k[5];
+  const float xq = to_f32(x[plane + h * P.W + w]);
+  float acc = g_gap_x ? g_gap_x[(size_t)b * P.C + ch] / (float)HW : 0.f;
+  const int ctr = P.R * P.dil;
+  for_each_preimage(h, P.H, P.pad, P.mode, [&](int pr) {
+    for_each_preimage(w, P.W, P.pad, P.mode, [&](int pc) {
+      // (1) q as the neighbour tap t of output pixel (i, j): i*stride + a*dil - pad == pr
+      for (int t = 0; t < P.K; ++t) {
+        int a, bb;
+        tap_rc(t, P.k, P.K, a, bb);
+        const int ti = pr + P.pad - a * P.dil, tj = pc + P.pad - bb * P.dil;
+        if (ti < 0 || tj < 0 || ti % P.stride || tj % P.stride) continue;
+        const int i = ti / P.stride, j = tj / P.stride;
+        if (i >= P.Ho || j >= P.Wo) continue;
+        const int rc = map_index(i * P.stride + ctr - P.pad, P.H, P.mode);
+        const int cc = map_index(j * P.stride + ctr - P.pad, P.W, P.mode);
+        const float c = (rc >= 0 && cc >= 0) ? to_f32(x[plane + rc * P.W + cc]) : 0.f;
+        const long long pb = (long long)b * P.K * HoWo + (long long)i * P.Wo + j + t * HoWo;
+        float k[5];
 #pragma unroll
-    for (int u = 0; u < 5; ++u) k[u] = coef[u * npairs + pbase + t * HoWo];
-    float dc, dn;
-    chan_grad<M>(c, n, k, P, dc, dn);
-    dc_sum += dc;
-    if (nvalid) atomicAdd(gx32 + plane + rn * P.W + cn, dn);
-  }
-  if (cvalid) atomicAdd(gx32 + plane + rc * P.W + cc, dc_sum);
-}
-
-__global__ void __launch_bounds__(kThreads) to_bf16_kernel(const float* __restrict__ src,
-                                                           __nv_bfloat16* __restrict__ dst, long long total) {
-  long long idx = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (idx < total) dst[idx] = __float2bfloat16_rn(src[idx]);
+        for (int u = 0; u < 5; ++u) k[u] = coef[u * npairs + pb];
+        float dc, dn;
+        chan_grad<M>(c, xq, k, P, dc, dn);
+        acc += dn;
+      }
+      // (2) q as the centre of output pixel (i, j): i*stride + R*dil - pad == pr
+      const int ti = pr + P.pad - ctr, tj = pc + P.pad - ctr;
+      if (ti >= 0 && tj >= 0 && ti % P.stride == 0 && tj % P.stride == 0) {
+        const int i = ti / P.stride, j = tj / P.stride;
+        if (i < P.Ho && j < P.Wo) {
+          const long long pb = (long long)b * P.K * HoWo + (long long)i * P.Wo + j;
+          for (int t = 0; t < P.K; ++t) {
+            int a, bb;
+            tap_rc(t, P.k, P.K, a, bb);
+            const int rn = map_index(i * P.stride + a * P.dil - P.pad, P.H, P.mode);
+            const int cn = map_index(j * P.stride + bb * P.dil - P.pad, P.W, P.mode);
+            const float n = (rn >= 0 && cn >= 0) ? to_f32(x[plane + rn * P.W + cn]) : 0.f;
+            float k[5];
+#pragma unroll
+            for (int u = 0; u < 5; ++u) k[u] = coef[u * npairs + pb + t * HoWo];
+            float dc, dn;
+            chan_grad<M>(xq, n, k, P, dc, dn);
+            acc += dc;
+          }
+        }
+      }
+    });
+  });
+  gx[idx] = from_f32<T>(acc);
 }
 
 // mean over the spatial plane: one warp per (b, channel)
@@ -572,19 +606,13 @@ int forward_t(const KParams& P, int measure, const T* x, T* y, const LaunchCtx& 
   return (int)cudaGetLastError();
 }
 
-// workspace layout of backward: [coef: 5*npairs f32][gx32: B*C*H*W f32, bf16 only]
+// workspace layout of backward: [coef: 5*npairs f32]
 template <typename T>
 int backward_t(const KParams& P, int measure, const T* x, const T* gy, T* gx, const float* g_gap_x,
                char* ws, cudaStream_t stream) {
   const long long npairs = (long long)P.B * P.K * P.Ho * P.Wo;
   const long long nx = (long long)P.B * P.C * P.H * P.W;
   float* coef = (float*)ws;
-  float* gx32;
-  if constexpr (sizeof(T) == 4) {
-    gx32 = (float*)gx;
-  } else {
-    gx32 = (float*)(ws + align256(sizeof(float) * 5 * (size_t)npairs));
-  }
   NFP_DISPATCH_MEASURE(measure,
     (pair_coef_kernel<T, M><<<blocks_for(npairs), kThreads, 0, stream>>>(x, gy, coef, P, npairs)));
   if (measure == NFPB200_ATTENTION) {
@@ -594,13 +622,8 @@ int backward_t(const KParams& P, int measure, const T* x, const T* gy, T* gx, co
     scs_coef_kernel_a<T><<<blocks_for(npairs), kThreads, 0, stream>>>(gy, coef, P, npairs);
     scs_coef_kernel_b<<<blocks_for(npairs), kThreads, 0, stream>>>(coef, P, npairs);
   }
-  init_grad_kernel<<<blocks_for(nx), kThreads, 0, stream>>>(gx32, g_gap_x, P.H * P.W, nx);
-  const long long total = (long long)P.B * P.C * P.Ho * P.Wo;
   NFP_DISPATCH_MEASURE(measure,
-    (scatter_kernel<T, M><<<blocks_for(total), kThreads, 0, stream>>>(x, coef, gx32, P, npairs, total)));
-  if constexpr (sizeof(T) == 2) {
-    to_bf16_kernel<<<blocks_for(nx), kThreads, 0, stream>>>(gx32, (__nv_bfloat16*)gx, nx);
-  }
+    (gather_kernel<T, M><<<blocks_for(nx), kThreads, 0, stream>>>(x, coef, gx, g_gap_x, P, npairs, nx)));
   return (int)cudaGetLastError();
 }
 
@@ -611,7 +634,8 @@ size_t generic_workspace_bytes(const KParams& P, int dtype, int measure, int op)
   const size_t nx = (size_t)P.B * P.C * P.H * P.W;
   const size_t esz = dtype == NFPB200_BF16 ? 2 : 4;
   const size_t fwd = measure == NFPB200_ATTENTION ? 4 * npairs : (measure == NFPB200_SCS ? 8 * npairs : 0);
-  const size_t bwd = align256(20 * npairs) + (dtype == NFPB200_BF16 ? align256(4 * nx) : 0);
+  const size_t bwd = align256(20 * npairs);
+  (void)nx;
   switch (op) {
     case NFPB200_OP_FORWARD: return fwd;
     case NFPB200_OP_BACKWARD: return bwd;
@@ -626,7 +650,8 @@ int generic_launch_count(const KParams& P, int dtype, int measure, int op) {
   const int extra_f = (measure == NFPB200_ATTENTION || measure == NFPB200_SCS) ? 1 : 0;
   const int extra_b = measure == NFPB200_ATTENTION ? 1 : (measure == NFPB200_SCS ? 2 : 0);
   const int fwd = 1 + extra_f;
-  const int bwd = 3 + extra_b + (dtype == NFPB200_BF16 ? 1 : 0);
+  const int bwd = 2 + extra_b;
+  (void)dtype;
   switch (op) {
     case NFPB200_OP_FORWARD: return fwd;
     case NFPB200_OP_BACKWARD: return bwd;
