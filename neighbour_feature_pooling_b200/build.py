@@ -36,13 +36,27 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
-def _deps():
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "nfp_b200.h")]
-    return max(os.path.getmtime(p) for p in deps)
+HASH_PATH = os.path.join(LIB_DIR, "libnfp_b200.so.srchash")
+
+
+def source_hash() -> str:
+    """sha256 over the contents of every source the library is built from (and the flags): the built .so is reused only
+    when this matches the hash recorded beside it -- a stale library shipped with newer sources is rebuilt, whatever
+    the file times say."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS[:6]).encode())
+    for path in sorted([os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "nfp_b200.h")]):
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
 
 
 def needs_build() -> bool:
-    return not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < _deps()
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
+        return True
+    with open(HASH_PATH) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False, variant: str = "", defines=()) -> str:
@@ -78,6 +92,9 @@ def build(force: bool = False, verbose: bool = False, variant: str = "", defines
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     os.replace(tmp, lib_path)
+    if not variant:
+        with open(HASH_PATH, "w") as f:
+            f.write(source_hash() + "\n")
     return lib_path
 
 

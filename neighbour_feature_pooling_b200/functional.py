@@ -107,7 +107,10 @@ def _trace(desc, op, what):
         PATH_TRACE.add(f"{_capi.describe_path(desc, op)} {'bf16' if desc.dtype == _capi.BF16 else 'f32'} "
                        f"{'channels-last' if desc.layout else 'nchw'} {what}")
 
-_X_STABLE_HINT = os.environ.get("NFPB200_X_STABLE_HINT", "1") != "0"
+# NFPB200_HINT_X_STABLE (include/nfp_b200.h) is opt-in: it pays only when the backward directly follows another fused NFP
+# launch on the stream (-1.9 us per backward in such chains); after any other kernel -- the normal case inside a network --
+# there is nothing to overlap and the reordered prologue costs ~0.9 us.  NFPB200_X_STABLE_HINT=1 switches it on.
+_X_STABLE_HINT = os.environ.get("NFPB200_X_STABLE_HINT", "0") == "1"
 
 
 def _prepare(x: torch.Tensor, cfg: NFPConfig = None):
@@ -224,10 +227,8 @@ class _NFPSimilarity(torch.autograd.Function):
     def backward(ctx, gy):
         (x,) = ctx.saved_tensors
         desc = _desc_for(x, ctx.cfg, ctx.layout)
-        # x is a saved forward activation: whatever NFP kernel precedes this launch on the stream did not write it,
-        # so the fused backward may stream it while that kernel drains (NFPB200_HINT_X_STABLE, include/nfp_b200.h).
-        # It pays when NFP launches are adjacent on the stream (-1.7 us per backward); after any other kernel there is
-        # nothing to overlap and the reordered prologue costs ~0.9 us.  NFPB200_X_STABLE_HINT=0 switches it off.
+        # x is a saved forward activation: the launch that precedes this one on the stream did not write it, so the
+        # hint would be valid here; see _X_STABLE_HINT for why it is opt-in
         if _X_STABLE_HINT:
             desc.path |= _capi.HINT_X_STABLE
         gy = gy.to(x.dtype).contiguous()
@@ -265,10 +266,8 @@ class _NFPGapPair(torch.autograd.Function):
     def backward(ctx, g_gap_x, g_gap_nfp):
         (x,) = ctx.saved_tensors
         desc = _desc_for(x, ctx.cfg, ctx.layout)
-        # x is a saved forward activation: whatever NFP kernel precedes this launch on the stream did not write it,
-        # so the fused backward may stream it while that kernel drains (NFPB200_HINT_X_STABLE, include/nfp_b200.h).
-        # It pays when NFP launches are adjacent on the stream (-1.7 us per backward); after any other kernel there is
-        # nothing to overlap and the reordered prologue costs ~0.9 us.  NFPB200_X_STABLE_HINT=0 switches it off.
+        # x is a saved forward activation: the launch that precedes this one on the stream did not write it, so the
+        # hint would be valid here; see _X_STABLE_HINT for why it is opt-in
         if _X_STABLE_HINT:
             desc.path |= _capi.HINT_X_STABLE
         g_gap_x = g_gap_x.float().contiguous()
