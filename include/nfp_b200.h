@@ -188,7 +188,7 @@ int nfpb200_pool_backward(const nfpb200_desc_t* desc, const void* x, const float
  *                                                                 proj_b (C) fp32 = nfp_proj.bias (NULL = none)
  * The forward also returns gap_x (B, C) and gap_nfp (B, K) (fp32): the backward reads them back, and the caller needs
  * them for the parameter gradients (d proj_w = (g_out * gap_x)^T gap_nfp, d proj_b = sum_b g_out * gap_x), which stay
- * on the caller's side.  Served by the fused NCHW kernels (cosine, pad = R, stride 1, shapes of the streaming path);
+ * on the caller's side.  Served by the fused NCHW ring kernels and the channels-last token kernels (cosine, pad = R, stride 1);
  * nfpb200_head_supported() returns NFPB200_OK when both directions are, NFPB200_EUNSUPPORTED otherwise -- then compose
  * nfpb200_pool_forward / _backward with the projection on the caller's side. */
 int nfpb200_head_supported(const nfpb200_desc_t* desc);

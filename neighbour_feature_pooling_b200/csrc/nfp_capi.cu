@@ -226,8 +226,10 @@ int nfpb200_pool_backward(const nfpb200_desc_t* desc, const void* x, const float
 
 // ---- fused nfp_pooling head -------------------------------------------------------------------------------------
 static int head_path(const nfpb200_desc_t* desc, const KParams& P, int pool_op) {
-  if (P.layout == NFPB200_LAYOUT_NHWC) return NFPB200_EUNSUPPORTED;
   const int want = desc->path & ~kPathFlags;
+  if (P.layout == NFPB200_LAYOUT_NHWC)
+    return (want != NFPB200_PATH_GENERIC && P.K % 4 == 0 && token_supported(P, desc->dtype, desc->measure, pool_op))
+               ? 4 : NFPB200_EUNSUPPORTED;
   if (want == NFPB200_PATH_GENERIC) return NFPB200_EUNSUPPORTED;
   return stream_head_supported(P, desc->dtype, desc->measure, pool_op) ? 2 : NFPB200_EUNSUPPORTED;
 }
@@ -254,6 +256,8 @@ int nfpb200_head_forward(const nfpb200_desc_t* desc, const void* x, const float*
   rc = head_path(desc, P, NFPB200_OP_POOL_FORWARD);
   if (rc < 0) return rc;
   LaunchCtx ctx{(cudaStream_t)stream, nullptr, 0};
+  if (rc == 4)
+    return token_head_run(P, NFPB200_OP_POOL_FORWARD, x, proj_w, proj_b, out, gap_x, gap_nfp, nullptr, nullptr, ctx);
   return stream_head_forward(P, desc->dtype, x, proj_w, proj_b, out, gap_x, gap_nfp, ctx);
 }
 
@@ -269,6 +273,9 @@ int nfpb200_head_backward(const nfpb200_desc_t* desc, const void* x, const float
   rc = head_path(desc, P, NFPB200_OP_POOL_BACKWARD);
   if (rc < 0) return rc;
   LaunchCtx ctx{(cudaStream_t)stream, nullptr, 0};
+  if (rc == 4)
+    return token_head_run(P, NFPB200_OP_POOL_BACKWARD, x, proj_w, proj_b, nullptr, const_cast<float*>(gap_x),
+                          const_cast<float*>(gap_nfp), g_out, gx, ctx);
   return stream_head_backward(P, desc->dtype, x, proj_w, proj_b, gap_x, gap_nfp, g_out, gx, ctx);
 }
 

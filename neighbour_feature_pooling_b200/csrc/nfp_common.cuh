@@ -99,6 +99,9 @@ const char* token_name(const KParams& P);
 int token_run(const KParams& P, int op, const void* x, const void* gy, void* y, void* gx, const float* g_gap_x,
               const float* g_gap_nfp, float* gap_x, float* gap_nfp, const LaunchCtx& ctx);
 
+int token_head_run(const KParams& P, int op, const void* x, const float* proj_w, const float* proj_b, float* out,
+                   float* gap_x, float* gap_nfp, const float* g_out, void* gx, const LaunchCtx& ctx);
+
 // planar kernels (cosine, stride 1, dilation 1, pad = R, any map size; map mode only): nfp_planar.cu
 bool planar_supported(const KParams& P, int dtype, int measure, int op);
 size_t planar_workspace_bytes(const KParams& P, int op);

@@ -55,6 +55,11 @@ struct TokenArgs {
   const float* g_gap_nfp;
   float* gap_x;
   float* gap_nfp;
+  // fused nfp_pooling head (NFP_Pooling.py:31-35), as in the NCHW ring kernels
+  const float* proj_w;     // (C, K) fp32, null = plain pooled mode
+  const float* proj_b;     // (C) fp32 or null
+  float* head_out;         // forward: (B, C) fp32
+  const float* head_gout;  // backward: d loss / d out (B, C) fp32; gap_x / gap_nfp then hold the forward's results
   int B, C;
   long long xbs, gxbs;  // batch strides of x / gx in elements
   int nbuf;             // image buffers in shared memory (1 or 2)
@@ -265,9 +270,47 @@ __global__ void __launch_bounds__(NW * 32, NW == kNWSmall ? 2 : 1) token_kernel(
       float* Gp = reinterpret_cast<float*>(smem_raw + L.gp);
       const unsigned char* g = smem_raw + L.gyraw + (POOLED ? 0 : bf * L.gy_stride);
       if constexpr (POOLED) {
-        if (tid < K) reinterpret_cast<float*>(smem_raw + L.gyraw)[tid] = a.g_gap_nfp[(size_t)b * K + tid] * (1.f / (float)P);
         float* gs = reinterpret_cast<float*>(smem_raw + L.ggx);
-        for (int i = tid; i < Cch; i += NT) gs[i] = a.g_gap_x[(size_t)b * Cch + i] * (1.f / (float)P);
+        if (a.proj_w) {
+          // fused head backward: d/d GAP(x)[c] = g_out[c] (proj_w[c] . gnfp + proj_b[c]),
+          // d/d GAP(NFP(x))[n] = sum_c g_out[c] GAP(x)[c] proj_w[c][n] (fixed-order block reduction)
+          float gn[K], part[K];
+#pragma unroll
+          for (int n = 0; n < K; ++n) {
+            gn[n] = a.gap_nfp[(size_t)b * K + n];
+            part[n] = 0.f;
+          }
+          for (int c = tid; c < Cch; c += NT) {
+            const float go = a.head_gout[(size_t)b * Cch + c], gxv = a.gap_x[(size_t)b * Cch + c];
+            const float4* wr4 = reinterpret_cast<const float4*>(a.proj_w + (size_t)c * K);
+            float proj = a.proj_b ? a.proj_b[c] : 0.f;
+            const float t = go * gxv;
+#pragma unroll
+            for (int n4 = 0; n4 < K / 4; ++n4) {
+              const float4 w4 = wr4[n4];
+              proj = fmaf(w4.x, gn[4 * n4], proj); proj = fmaf(w4.y, gn[4 * n4 + 1], proj);
+              proj = fmaf(w4.z, gn[4 * n4 + 2], proj); proj = fmaf(w4.w, gn[4 * n4 + 3], proj);
+              part[4 * n4] = fmaf(t, w4.x, part[4 * n4]); part[4 * n4 + 1] = fmaf(t, w4.y, part[4 * n4 + 1]);
+              part[4 * n4 + 2] = fmaf(t, w4.z, part[4 * n4 + 2]); part[4 * n4 + 3] = fmaf(t, w4.w, part[4 * n4 + 3]);
+            }
+            gs[c] = go * proj * (1.f / (float)P);
+          }
+#pragma unroll
+          for (int n = 0; n < K; ++n) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part[n] += __shfl_xor_sync(0xffffffffu, part[n], o);
+            if (lane == 0) Gp[warp * K + n] = part[n];   // Gp is free until the stencil loops below
+          }
+          __syncthreads();
+          if (tid < K) {
+            float sred = 0.f;
+            for (int w = 0; w < NW; ++w) sred += Gp[w * K + tid];
+            reinterpret_cast<float*>(smem_raw + L.gyraw)[tid] = sred * (1.f / (float)P);
+          }
+        } else {
+          if (tid < K) reinterpret_cast<float*>(smem_raw + L.gyraw)[tid] = a.g_gap_nfp[(size_t)b * K + tid] * (1.f / (float)P);
+          for (int i = tid; i < Cch; i += NT) gs[i] = a.g_gap_x[(size_t)b * Cch + i] * (1.f / (float)P);
+        }
         __syncthreads();
       }
       auto Gv = [&](int flat) -> float {
@@ -422,7 +465,25 @@ __global__ void __launch_bounds__(NW * 32, NW == kNWSmall ? 2 : 1) token_kernel(
           for (int p = lane; p < P; p += 32) s += ytab[n * P + p];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          if (lane == 0) a.gap_nfp[(size_t)b * K + n] = s / (float)P;
+          if (lane == 0) {
+            a.gap_nfp[(size_t)b * K + n] = s / (float)P;
+            tfull[n] = s / (float)P;   // (the table is dead: every y value has been computed)
+          }
+        }
+        if (a.proj_w) {
+          // fused head: out[c] = GAP(x)[c] * (proj_w[c] . GAP(NFP(x)) + proj_b[c])
+          __syncthreads();   // tfull[0..K) and this CTA's gap_x stores are visible to the whole CTA
+          for (int c = tid; c < Cch; c += NT) {
+            const float4* wr4 = reinterpret_cast<const float4*>(a.proj_w + (size_t)c * K);
+            float proj = a.proj_b ? a.proj_b[c] : 0.f;
+#pragma unroll
+            for (int n4 = 0; n4 < K / 4; ++n4) {
+              const float4 w4 = wr4[n4];
+              proj = fmaf(w4.x, tfull[4 * n4], proj); proj = fmaf(w4.y, tfull[4 * n4 + 1], proj);
+              proj = fmaf(w4.z, tfull[4 * n4 + 2], proj); proj = fmaf(w4.w, tfull[4 * n4 + 3], proj);
+            }
+            a.head_out[(size_t)b * Cch + c] = a.gap_x[(size_t)b * Cch + c] * proj;
+          }
         }
       }
     } else {
@@ -688,6 +749,20 @@ const char* token_name(const KParams& P) {
   NFP_STREAM_SHAPES(X)
 #undef X
   return nm;
+}
+
+int token_head_run(const KParams& P, int op, const void* x, const float* proj_w, const float* proj_b, float* out,
+                   float* gap_x, float* gap_nfp, const float* g_out, void* gx, const LaunchCtx& ctx) {
+  token::TokenArgs a{};
+  a.x = x; a.gx = gx; a.gap_x = gap_x; a.gap_nfp = gap_nfp;
+  a.proj_w = proj_w; a.proj_b = proj_b; a.head_out = out; a.head_gout = g_out;
+  a.B = P.B; a.C = P.C;
+  const long long dense = (long long)P.H * P.W * P.C;
+  a.xbs = P.x_batch_stride > 0 ? P.x_batch_stride : dense;
+  a.gxbs = P.gx_batch_stride > 0 ? P.gx_batch_stride : dense;
+  a.pad_mode = P.mode; a.similarity = P.similarity; a.eps = P.eps; a.y_f32 = 0;
+  a.dbg = stream::g_debug_stamps;
+  return token::launch(P, token_mode(op), a, ctx.stream);
 }
 
 int token_run(const KParams& P, int op, const void* x, const void* gy, void* y, void* gx, const float* g_gap_x,

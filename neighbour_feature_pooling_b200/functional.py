@@ -287,8 +287,8 @@ class _NFPHead(torch.autograd.Function):
     parameter gradients are three tiny PyTorch ops on the (B, C) / (B, K) tensors the forward leaves behind."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, cfg):
-        desc = _desc_for(x, cfg)
+    def forward(ctx, x, weight, bias, cfg, layout=0):
+        desc = _desc_for(x, cfg, layout)
         B, C = x.shape[:2]
         w = weight.detach().float().contiguous()
         bvec = bias.detach().float().contiguous() if bias is not None else None
@@ -297,7 +297,8 @@ class _NFPHead(torch.autograd.Function):
         gap_nfp = torch.empty((B, cfg.out_channels), dtype=torch.float32, device=x.device)
         if PATH_TRACE is not None:
             PATH_TRACE.add(f"{_capi.describe_path(desc, _capi.OP_POOL_FORWARD)} "
-                           f"{'bf16' if desc.dtype == _capi.BF16 else 'f32'} nchw fused head (GAP, GAP(NFP), proj, product)")
+                           f"{'bf16' if desc.dtype == _capi.BF16 else 'f32'} {'channels-last' if layout else 'nchw'} "
+                           "fused head (GAP, GAP(NFP), proj, product)")
         with torch.cuda.device(x.device):
             rc = _capi.load().nfpb200_head_forward(ctypes.byref(desc), x.data_ptr(), w.data_ptr(),
                                                    bvec.data_ptr() if bvec is not None else None, out.data_ptr(),
@@ -305,6 +306,7 @@ class _NFPHead(torch.autograd.Function):
         _capi.check(rc, "nfpb200_head_forward")
         ctx.save_for_backward(x, w, bvec if bvec is not None else w.new_empty(0), gap_x, gap_nfp)
         ctx.cfg = cfg
+        ctx.layout = layout
         ctx.has_bias = bias is not None
         ctx.param_dtypes = (weight.dtype, bias.dtype if bias is not None else None)
         return out
@@ -313,11 +315,11 @@ class _NFPHead(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_out):
         x, w, bvec, gap_x, gap_nfp = ctx.saved_tensors
-        desc = _desc_for(x, ctx.cfg)
+        desc = _desc_for(x, ctx.cfg, ctx.layout)
         if _X_STABLE_HINT:
             desc.path |= _capi.HINT_X_STABLE
         g_out = g_out.float().contiguous()
-        gx = torch.empty_like(x)
+        gx = _empty_like_layout(x, ctx.layout)
         with torch.cuda.device(x.device):
             rc = _capi.load().nfpb200_head_backward(ctypes.byref(desc), x.data_ptr(), w.data_ptr(),
                                                     bvec.data_ptr() if ctx.has_bias else None, gap_x.data_ptr(),
@@ -327,7 +329,7 @@ class _NFPHead(torch.autograd.Function):
         t = g_out * gap_x                                   # d loss / d proj  (B, C)
         gw = (t.t() @ gap_nfp).to(ctx.param_dtypes[0]) if ctx.needs_input_grad[1] else None
         gb = t.sum(0).to(ctx.param_dtypes[1]) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
 
 
 def nfp_head(x: torch.Tensor, weight: torch.Tensor, bias, cfg: NFPConfig):
@@ -337,12 +339,10 @@ def nfp_head(x: torch.Tensor, weight: torch.Tensor, bias, cfg: NFPConfig):
         return None
     _check_geometry(x.shape[2], x.shape[3], cfg)
     xk, out_dtype, layout = _prepare(x, cfg)
-    if layout != _capi.LAYOUT_NCHW:
-        return None
-    desc = _desc_for(xk, cfg)
+    desc = _desc_for(xk, cfg, layout)
     if _capi.load().nfpb200_head_supported(ctypes.byref(desc)) != 0:
         return None
-    out = _NFPHead.apply(xk, weight, bias, cfg)
+    out = _NFPHead.apply(xk, weight, bias, cfg, layout)
     # NFP_Pooling.py:35: x_avg (dtype of x) * nfp_proj(...) (autocast dtype under autocast, else the parameter dtype)
     proj_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else weight.dtype
     return out.to(torch.promote_types(x.dtype, proj_dtype))

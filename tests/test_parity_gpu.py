@@ -753,3 +753,41 @@ def test_fused_head_matches_composition_and_oracle(shape, dtype, cuda_device):
     out2.backward(g.to(cuda_device, out2.dtype))
     assert rel_err(out2.detach().float().cpu(), out.detach().float().cpu()) < (1e-5 if dtype == torch.float32 else 2e-2)
     assert rel_err(x2.grad.float().cpu(), xd.grad.float().cpu()) < (1e-5 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("shape", [(5, 64, 7, 7, 1), (3, 512, 7, 7, 1), (2, 960, 7, 7, 1), (3, 192, 14, 14, 1),
+                                   (6, 512, 2, 2, 1), (3, 128, 7, 7, 2)],
+                         ids=lambda s: "x".join(map(str, s[:4])) + f"_r{s[4]}")
+def test_fused_head_channels_last(shape, cuda_device):
+    """The fused nfp_pooling head on the channels-last tensor-core kernels (what the training steps of bench_train.py
+    run): output and the gradients of x, nfp_proj.weight and nfp_proj.bias against the oracle."""
+    B, C, H, W, R = shape
+    K = (2 * R + 1) ** 2 - 1
+    gen = torch.Generator().manual_seed(2 * B + C + H)
+    x = torch.randn(B, C, H, W, generator=gen).bfloat16().float()
+    g = torch.randn(B, C, generator=gen)
+    params = {"num_ftrs": {"m": C}, "Model_name": "m", "Dataset": "d", "num_classes": {"d": 3}}
+    torch.manual_seed(11)
+    head = nfp_pooling(nfp_layer=NFPPooling(C, R=R, measure="cosine", padding=R), Params=params).to(cuda_device)
+    Wp, bp = head.nfp_proj.weight.detach().cpu().double(), head.nfp_proj.bias.detach().cpu().double()
+    xr = x.double()
+    y_map = torch.as_tensor(np.asarray(O.nfp_forward(xr, R=R, measure="cosine", padding=R)))
+    gap_n, gap_x = y_map.mean((2, 3)), xr.mean((2, 3))
+    proj = gap_n @ Wp.t() + bp
+    out_ref = gap_x * proj
+    t = g.double() * gap_x
+    gy = ((t @ Wp) / (H * W))[:, :, None, None].expand(B, K, H, W).contiguous()
+    _, gx_map = O.nfp_forward_backward(xr, gy, R=R, measure="cosine", padding=R)
+    gx_ref = torch.as_tensor(np.asarray(gx_map)) + ((g.double() * proj) / (H * W))[:, :, None, None]
+    xd = x.to(cuda_device, torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    NF.PATH_TRACE = set()
+    try:
+        out = head(xd)
+    finally:
+        paths, NF.PATH_TRACE = NF.PATH_TRACE, None
+    assert any("fused/token" in p and "channels-last fused head" in p for p in paths), paths
+    out.backward(g.to(cuda_device, out.dtype))
+    assert rel_err(out.detach().float().cpu(), out_ref) < BF16_TOL
+    assert rel_err(xd.grad.float().cpu(), gx_ref) < BF16_TOL
+    assert rel_err(head.nfp_proj.weight.grad.cpu(), t.t() @ gap_n) < BF16_TOL
+    assert rel_err(head.nfp_proj.bias.grad.cpu(), t.sum(0)) < BF16_TOL
