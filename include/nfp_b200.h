@@ -25,7 +25,10 @@
  *     errors, a positive cudaError_t for CUDA failures.  No C++ exception
  *     crosses the boundary.  nfpb200_status_string() renders either.
  *   - re-entrant and thread-safe: no global mutable state besides one-time
- *     cudaFuncSetAttribute calls.
+ *     cudaFuncSetAttribute calls, the (atomic) diagnostics pointer of
+ *     nfpb200_debug_phase_timing, and the NFPB200_* tuning environment variables
+ *     (INTEGRATION.md section 5), which are read ONCE, at the first launch that
+ *     consults them, and never change behaviour afterwards.
  *   - sm_100a only.  There is no CPU path in this library.
  */
 #ifndef NFP_B200_H_
@@ -149,7 +152,8 @@ const char* nfpb200_status_string(int status);
 /* Diagnostics: when `device_stamps` is non-null, every fused-kernel CTA records 8 x uint64 nanosecond
  * timestamps (%globaltimer) of its phase boundaries for its first image at device_stamps[8 * blockIdx.x + k]
  * (k = 0 consumers ready, 1 pass A done, 2 forward written / coefficients ready, 3 pass B done, 4 stores
- * drained).  The buffer must hold 8 * (number of CTAs) entries; pass NULL to switch it off.  Not thread-safe. */
+ * drained; the cluster-split and token kernels stamp two work items per CTA: 16 entries per CTA).  The buffer must hold
+ * 16 * (number of CTAs) entries; pass NULL to switch it off.  Diagnostics only: the pointer is process-wide (atomic). */
 int nfpb200_debug_phase_timing(unsigned long long* device_stamps);
 
 /* (H', W') = Conv2d output size for the descriptor's geometry; validates the descriptor. */

@@ -118,7 +118,7 @@ const char* nfpb200_status_string(int status) {
 }
 
 int nfpb200_debug_phase_timing(unsigned long long* device_stamps) {
-  nfp::stream::g_debug_stamps = device_stamps;
+  nfp::stream::g_debug_stamps.store(device_stamps, std::memory_order_relaxed);
   return NFPB200_OK;
 }
 

@@ -8,7 +8,7 @@
 
 namespace nfp {
 namespace stream {
-unsigned long long* g_debug_stamps = nullptr;
+std::atomic<unsigned long long*> g_debug_stamps{nullptr};
 }
 namespace {
 
@@ -46,13 +46,13 @@ int run(const KParams& P, int dtype, int mode, stream::StreamArgs a, cudaStream_
     sa.pad_mode = P.mode; sa.similarity = P.similarity; sa.eps = P.eps;
     sa.x_early = a.x_early;
     sa.y_f32 = P.y_f32;
-    sa.dbg = stream::g_debug_stamps;
+    sa.dbg = stream::g_debug_stamps.load(std::memory_order_relaxed);
     return dtype == NFPB200_BF16 ? split::launch_bf16(P, mode, sa, s) : split::launch_f32(P, mode, sa, s);
   }
   a.B = P.B; a.C = P.C;
   a.pad_mode = P.mode; a.similarity = P.similarity; a.eps = P.eps;
   a.y_f32 = P.y_f32;
-  a.dbg = stream::g_debug_stamps;
+  a.dbg = stream::g_debug_stamps.load(std::memory_order_relaxed);
   return dtype == NFPB200_BF16 ? stream::launch_bf16(P, mode, a, s) : stream::launch_f32(P, mode, a, s);
 }
 

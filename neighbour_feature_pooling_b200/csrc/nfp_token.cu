@@ -761,7 +761,7 @@ int token_head_run(const KParams& P, int op, const void* x, const float* proj_w,
   a.xbs = P.x_batch_stride > 0 ? P.x_batch_stride : dense;
   a.gxbs = P.gx_batch_stride > 0 ? P.gx_batch_stride : dense;
   a.pad_mode = P.mode; a.similarity = P.similarity; a.eps = P.eps; a.y_f32 = 0;
-  a.dbg = stream::g_debug_stamps;
+  a.dbg = stream::g_debug_stamps.load(std::memory_order_relaxed);
   return token::launch(P, token_mode(op), a, ctx.stream);
 }
 
@@ -775,7 +775,7 @@ int token_run(const KParams& P, int op, const void* x, const void* gy, void* y, 
   a.xbs = P.x_batch_stride > 0 ? P.x_batch_stride : dense;
   a.gxbs = P.gx_batch_stride > 0 ? P.gx_batch_stride : dense;
   a.pad_mode = P.mode; a.similarity = P.similarity; a.eps = P.eps; a.y_f32 = P.y_f32;
-  a.dbg = stream::g_debug_stamps;
+  a.dbg = stream::g_debug_stamps.load(std::memory_order_relaxed);
   return token::launch(P, token_mode(op), a, ctx.stream);
 }
 
