@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define NFPB200_ABI_VERSION 2
+#define NFPB200_ABI_VERSION 3
 
 /* element type of x / y / gy / gx.  Accumulation is always fp32. */
 enum { NFPB200_F32 = 0, NFPB200_BF16 = 1 };
@@ -139,7 +139,15 @@ typedef struct nfpb200_desc {
   float q_scs;              /* nfp.py:34 */
   int32_t path;             /* NFPB200_PATH_* [| NFPB200_HINT_X_STABLE] [| NFPB200_FLAG_Y_F32] */
   int32_t layout;           /* NFPB200_LAYOUT_*; 0 = NCHW */
-  int32_t reserved0;        /* must be 0 */
+  int32_t inner_R;          /* multi-radius maps in one launch (models/nfp_heads.py:80-118, MultiRadiusNFPHead with
+                               R_list = (1, 2)): 0 = off; r in [1, R) = y / gy carry K_r + K channels per image, the map
+                               of radius r (padding r, K_r = (2r+1)^2 - 1 taps) FIRST, then the map of radius R -- the
+                               layout of torch.cat([NFP_r(x), NFP_R(x)], dim=1).  With padding = R (and r) the window of
+                               radius r is the inner part of the window of radius R under reflect / replicate / zero
+                               padding alike, so both maps come out of ONE pass over x, and the backward folds both
+                               gradient blocks into one stencil.  nfpb200_forward / nfpb200_backward on the fused
+                               (NCHW ring and channels-last token) kernels only; anything else: NFPB200_EUNSUPPORTED,
+                               and the caller issues one launch per radius */
   int64_t x_batch_stride;   /* NHWC only: elements between consecutive images of x; 0 = dense (H*W*C); multiple of 8 */
   int64_t gx_batch_stride;  /* NHWC only: the same for gx */
 } nfpb200_desc_t;
@@ -169,7 +177,7 @@ int nfpb200_describe_path(const nfpb200_desc_t* desc, int32_t op, char* buf, siz
 /* Number of kernel launches the op issues on `stream` (bench.py's gpu_launches). */
 int nfpb200_launch_count(const nfpb200_desc_t* desc, int32_t op, int32_t* launches);
 
-/* y (B, K, H', W') = NFP(x).  */
+/* y (B, K, H', W') = NFP(x)   (desc->inner_R = r > 0: (B, K_r + K, H, W), see nfpb200_desc_t).  */
 int nfpb200_forward(const nfpb200_desc_t* desc, const void* x, void* y,
                     void* workspace, size_t workspace_bytes, void* stream);
 

@@ -20,8 +20,9 @@ import sys
 import types
 
 from . import _capi, functional
-from .functional import NFPConfig, nfp_gap_pair, nfp_similarity
-from .modules import EnhancedNFPPooling, NFPPooling, nfp_pooling
+from .functional import NFPConfig, nfp_gap_pair, nfp_multi_radius, nfp_similarity
+from .modules import (EnhancedNFPPooling, MultiRadiusNFP, NFPPooling, fuse_multi_radius, nfp_pooling,
+                      unfuse_multi_radius)
 
 __version__ = "0.1.0"
 
@@ -66,4 +67,5 @@ def library_path() -> str:
 
 
 __all__ = ["NFPPooling", "EnhancedNFPPooling", "nfp_pooling", "NFPConfig", "nfp_similarity", "nfp_gap_pair",
+           "nfp_multi_radius", "MultiRadiusNFP", "fuse_multi_radius", "unfuse_multi_radius",
            "install_dropin", "uninstall_dropin", "library_path", "functional"]

@@ -15,7 +15,7 @@ import threading
 _LIB_PATH = os.environ.get("NFPB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
                                                           "libnfp_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 F32, BF16 = 0, 1
 PAD_MODES = {"zeros": 0, "reflect": 1, "replicate": 2, "circular": 3}
@@ -49,7 +49,7 @@ class Desc(ctypes.Structure):
         ("similarity", ctypes.c_int32), ("difference_taps", ctypes.c_int32),
         ("eps", ctypes.c_float), ("p", ctypes.c_float), ("q_scs", ctypes.c_float),
         ("path", ctypes.c_int32),
-        ("layout", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("layout", ctypes.c_int32), ("inner_R", ctypes.c_int32),
         ("x_batch_stride", ctypes.c_int64), ("gx_batch_stride", ctypes.c_int64),
     ]
 
@@ -124,7 +124,7 @@ def check(rc: int, what: str):
 def make_desc(dtype: int, B: int, C: int, H: int, W: int, R: int, stride: int, padding: int,
               dilation: int, padding_mode: str, measure: str, similarity: bool,
               difference_taps: bool, eps: float, p: float, q_scs: float, path: str = "auto",
-              layout: int = 0, x_batch_stride: int = 0, gx_batch_stride: int = 0) -> Desc:
+              layout: int = 0, x_batch_stride: int = 0, gx_batch_stride: int = 0, inner_R: int = 0) -> Desc:
     d = Desc()
     d.struct_bytes = ctypes.sizeof(Desc)
     d.dtype = dtype
@@ -139,7 +139,7 @@ def make_desc(dtype: int, B: int, C: int, H: int, W: int, R: int, stride: int, p
     d.q_scs = float(q_scs)
     d.path = PATHS[path]
     d.layout = layout
-    d.reserved0 = 0
+    d.inner_R = inner_R   # multi-radius launch: y / gy = [radius inner_R map | radius R map] (0 = off)
     d.x_batch_stride = x_batch_stride
     d.gx_batch_stride = gx_batch_stride
     return d

@@ -35,7 +35,9 @@ int make_params(const nfpb200_desc_t* d, KParams* out) {
   P.Ho = (P.H + 2 * P.pad - span) / P.stride + 1;
   P.Wo = (P.W + 2 * P.pad - span) / P.stride + 1;
   if (d->layout != NFPB200_LAYOUT_NCHW && d->layout != NFPB200_LAYOUT_NHWC) return NFPB200_EINVAL;
-  if (d->reserved0 != 0 || d->x_batch_stride < 0 || d->gx_batch_stride < 0) return NFPB200_EINVAL;
+  if (d->inner_R < 0 || d->inner_R >= d->R || d->x_batch_stride < 0 || d->gx_batch_stride < 0) return NFPB200_EINVAL;
+  P.rin = d->inner_R;
+  P.Kin = d->inner_R ? (2 * d->inner_R + 1) * (2 * d->inner_R + 1) - 1 : 0;
   P.layout = d->layout;
   P.x_batch_stride = d->x_batch_stride;
   P.gx_batch_stride = d->gx_batch_stride;
@@ -64,6 +66,13 @@ int make_params(const nfpb200_desc_t* d, KParams* out) {
 
 // 4 = token (channels-last), 3 = planar, 2 = fused (cluster-split or streaming-ring kernels), 0 = generic, <0 = error
 int choose_path(const nfpb200_desc_t* d, const KParams& P, int op) {
+  if (P.rin) {  // multi-radius launch: the fused kernels' map modes or nothing
+    if (op != NFPB200_OP_FORWARD && op != NFPB200_OP_BACKWARD) return NFPB200_EUNSUPPORTED;
+    const int want = d->path & ~kPathFlags;
+    if (want == NFPB200_PATH_GENERIC || want == NFPB200_PATH_SPLIT) return NFPB200_EUNSUPPORTED;
+    if (P.layout == NFPB200_LAYOUT_NHWC) return token_supported(P, d->dtype, d->measure, op) ? 4 : NFPB200_EUNSUPPORTED;
+    return stream_supported(P, d->dtype, d->measure, op) ? 2 : NFPB200_EUNSUPPORTED;
+  }
   if (P.layout == NFPB200_LAYOUT_NHWC) {
     if ((d->path & ~kPathFlags) == NFPB200_PATH_GENERIC) return NFPB200_EUNSUPPORTED;
     return token_supported(P, d->dtype, d->measure, op) ? 4 : NFPB200_EUNSUPPORTED;
@@ -227,6 +236,7 @@ int nfpb200_pool_backward(const nfpb200_desc_t* desc, const void* x, const float
 // ---- fused nfp_pooling head -------------------------------------------------------------------------------------
 static int head_path(const nfpb200_desc_t* desc, const KParams& P, int pool_op) {
   const int want = desc->path & ~kPathFlags;
+  if (P.rin) return NFPB200_EUNSUPPORTED;  // multi-radius launches exist in map mode only
   if (P.layout == NFPB200_LAYOUT_NHWC)
     return (want != NFPB200_PATH_GENERIC && P.K % 4 == 0 && token_supported(P, desc->dtype, desc->measure, pool_op))
                ? 4 : NFPB200_EUNSUPPORTED;

@@ -25,6 +25,7 @@ struct KParams {
   int force_split;      // NFPB200_PATH_SPLIT: the cluster-split kernels or nothing
   int y_f32;            // NFPB200_FLAG_Y_F32: forward writes y as fp32 although x is bf16
   int x_stable;         // NFPB200_HINT_X_STABLE: x is not an output of the launch that precedes this one
+  int rin, Kin;         // multi-radius launch (desc.inner_R): inner radius r (0 = off) and its tap count (2r+1)^2 - 1
   float eps, p, q;
 };
 
@@ -38,6 +39,17 @@ __host__ __device__ __forceinline__ int map_index(int i, int n, int mode) {
     case NFPB200_PAD_CIRCULAR:  return i < 0 ? i + n : i - n;
     default:                    return -1;
   }
+}
+
+// Multi-radius launches (desc.inner_R): tap n of the radius-R window (row-major, centre removed) -> the tap number of the
+// same offset in the radius-r window, or -1 when the offset lies outside it.  With padding = radius both windows see the
+// same padded pixel at the same offset (reflect / replicate / zeros map an index, whatever the pad width is).
+__host__ __device__ __forceinline__ int inner_tap(int n, int R, int r) {
+  const int k = 2 * R + 1, o = n < (k * k) / 2 ? n : n + 1;
+  const int dy = o / k - R, dx = o % k - R;
+  if (dy < -r || dy > r || dx < -r || dx > r) return -1;
+  const int k1 = 2 * r + 1, o1 = (dy + r) * k1 + dx + r;
+  return o1 < (k1 * k1) / 2 ? o1 : o1 - 1;
 }
 
 // tap index t in [0,K) -> (row a, col b) of the k x k window, centre removed, row-major (nfp.py:64-67)

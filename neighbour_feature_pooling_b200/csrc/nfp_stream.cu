@@ -34,6 +34,7 @@ bool split_ok(const KParams& P, int dtype, int mode) {
     return e && strcmp(e, "split") == 0;
   }();
   if (!want_split && !P.force_split) return false;
+  if (P.rin) return false;  // multi-radius launches: ring kernels only
   return (dtype == NFPB200_BF16 ? split::plan_bf16(P, mode) : split::plan_f32(P, mode)).ok;
 }
 
@@ -52,6 +53,7 @@ int run(const KParams& P, int dtype, int mode, stream::StreamArgs a, cudaStream_
   a.B = P.B; a.C = P.C;
   a.pad_mode = P.mode; a.similarity = P.similarity; a.eps = P.eps;
   a.y_f32 = P.y_f32;
+  a.kin = P.Kin; a.rin = P.rin;
   a.dbg = stream::g_debug_stamps.load(std::memory_order_relaxed);
   return dtype == NFPB200_BF16 ? stream::launch_bf16(P, mode, a, s) : stream::launch_f32(P, mode, a, s);
 }

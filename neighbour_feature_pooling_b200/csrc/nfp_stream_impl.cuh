@@ -80,7 +80,8 @@ struct Smem {
   int rn, wd, gp;                              // backward: 1/(N |x|) per pixel, stencil coefficients, stencil-warp scratch
   int wtab, stg, ytab;                         // inside the union
   int stg_warp;                                // staging bytes per warp (two buffers)
-  __host__ __device__ Smem(int CC, int nst, int Cfull) {
+  int gyin, gyin_stride;                       // multi-radius backward: the inner radius' gradient block (two images in flight)
+  __host__ __device__ Smem(int CC, int nst, int Cfull, int kin = 0) {
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 127) & ~127; return r; };
     // everything whose size is known at compile time comes first (so its address is a constant in the
@@ -122,6 +123,8 @@ struct Smem {
     lead = take(kLeadPad);
     ring = take(nst * slot_stride);
     ggx = take(MODE == MODE_POOL_BWD ? 2 * Cfull * 4 : 0);  // pooled backward: d out / d GAP(x) of two images in flight
+    gyin_stride = align_up(kin * C::P * ESZ, 16);
+    gyin = take(MODE == MODE_BWD ? 2 * gyin_stride : 0);
     total = o;
   }
 };
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int nst = a.nst, NCH = a.NCH, CC = a.CC;
-  const Smem<T, C, MODE, NW> L(CC, nst, a.C);
+  const Smem<T, C, MODE, NW> L(CC, nst, a.C, a.kin);
   unsigned char* ring = smem_raw + L.ring;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
   uint64_t* empty = full + kMaxStages;
@@ -207,9 +210,12 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
         if (MODE == MODE_BWD) {
           const int par = img & 1;
           mbar_wait(&gyempty[par], ((img >> 1) & 1) ^ 1);
-          mbar_expect_tx(&gyfull[par], (uint32_t)GY_BYTES);
-          bulk_g2s(smem_raw + L.gyraw + par * GY_STRIDE, reinterpret_cast<const T*>(a.gy) + (size_t)b * K * P,
-                   (uint32_t)GY_BYTES, &gyfull[par]);
+          // multi-radius launch: the image's gradient is [kin inner-radius planes | K planes]; two copies, one barrier
+          const uint32_t gin_bytes = (uint32_t)(a.kin * P * ESZ);
+          const T* gb = reinterpret_cast<const T*>(a.gy) + (size_t)b * (K + a.kin) * P;
+          mbar_expect_tx(&gyfull[par], (uint32_t)GY_BYTES + gin_bytes);
+          bulk_g2s(smem_raw + L.gyraw + par * GY_STRIDE, gb + a.kin * P, (uint32_t)GY_BYTES, &gyfull[par]);
+          if (gin_bytes) bulk_g2s(smem_raw + L.gyin + par * L.gyin_stride, gb, gin_bytes, &gyfull[par]);
         }
         if (MODE == MODE_POOL_BWD && a.ggx_tma) {  // the image's d out / d GAP(x): C floats, one bulk copy
           const int par = img & 1;
@@ -362,9 +368,20 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
       } else {
         mbar_wait(&gyfull[par], (img >> 1) & 1);
       }
+      const unsigned char* gin = smem_raw + L.gyin + par * L.gyin_stride;
       auto G = [&](int flat) -> float {  // upstream gradient element n*P + p
-        if constexpr (POOLED) return reinterpret_cast<const float*>(smem_raw + L.gyraw)[flat / P];
-        else return ldx<T>(g + flat * ESZ);
+        if constexpr (POOLED) {
+          return reinterpret_cast<const float*>(smem_raw + L.gyraw)[flat / P];
+        } else {
+          float v = ldx<T>(g + flat * ESZ);
+          if constexpr (R >= 2) {
+            if (a.kin) {  // multi-radius launch: the same tap of the inner radius' map adds its gradient
+              const int n = flat / P, n1 = inner_tap(n, R, a.rin);
+              if (n1 >= 0) v += ldx<T>(gin + (n1 * P + flat - n * P) * ESZ);
+            }
+          }
+          return v;
+        }
       };
       // G'[p][o] = gradient of the taps of p that land on p + off(o): the direct tap ...
       for (int idx = tid; idx < P * KK; idx += NT) {
@@ -577,8 +594,19 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
         if constexpr (POOLED) {
           ytab[idx] = yv;
         } else {
-          if (a.y_f32) reinterpret_cast<float*>(a.y)[(size_t)b * K * P + idx] = yv;
-          else reinterpret_cast<T*>(a.y)[(size_t)b * K * P + idx] = from_f32<T>(yv);
+          // (multi-radius launch: kin planes of the inner radius in front; its taps are the inner taps of this window)
+          const size_t yb = (size_t)b * (K + a.kin) * P;
+          if (a.y_f32) reinterpret_cast<float*>(a.y)[yb + a.kin * P + idx] = yv;
+          else reinterpret_cast<T*>(a.y)[yb + a.kin * P + idx] = from_f32<T>(yv);
+          if constexpr (R >= 2) {
+            if (a.kin) {
+              const int n1 = inner_tap(idx / P, R, a.rin);
+              if (n1 >= 0) {
+                if (a.y_f32) reinterpret_cast<float*>(a.y)[yb + n1 * P + p] = yv;
+                else reinterpret_cast<T*>(a.y)[yb + n1 * P + p] = from_f32<T>(yv);
+              }
+            }
+          }
         }
       }
       if constexpr (POOLED) {
@@ -981,6 +1009,7 @@ Plan plan_for(const KParams& P) {
   constexpr int pair = 2 * C::CPW;  // work item: a pair of channel groups
   if (((size_t)pair * C::P * esz) % 16) return pl;   // TMA bulk store / load granularity
   if (((size_t)C::K * C::P * esz) % 16) return pl;
+  if (P.Kin && (C::R < 2 || ((size_t)P.Kin * C::P * esz) % 16)) return pl;  // multi-radius: the blocks of gy are bulk-copied
   if (P.C % pair) return pl;
   // backward of the full-row-strip 3x3 shapes: lane-per-channel pass B when C is a whole number of 64-channel tasks
   // (NFPB200_PASSB_LANECH=0 keeps the strip form for A/B runs)
@@ -1003,7 +1032,7 @@ Plan plan_for(const KParams& P) {
     const int budget = kSmemPerSM / ctas - 2048;  // the runtime reserves 1 KB per CTA; 1 KB slack
     static const int max_stages = env_int("NFPB200_MAX_STAGES", 5);  // measured: 4-5 stages beat 6-8 at B = 256
     for (int nst = max_stages < kMaxStages ? max_stages : kMaxStages; nst >= 2; --nst) {  // as many stages as fit
-      Smem<T, C, MODE, kNW> L(pl.CC, nst, P.C);
+      Smem<T, C, MODE, kNW> L(pl.CC, nst, P.C, P.Kin);
       if (L.total > budget) continue;
       pl.nst = nst;
       pl.smem = (size_t)L.total;

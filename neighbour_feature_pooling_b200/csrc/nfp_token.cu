@@ -65,6 +65,7 @@ struct TokenArgs {
   int nbuf;             // image buffers in shared memory (1 or 2)
   int KS, KSlog;        // channel split of the Gram phase (a power of two) and its log2
   int pad_mode, similarity, y_f32;
+  int kin, rin;         // multi-radius launch (desc.inner_R): kin planes of the radius-rin map in front of y / gy
   float eps;
   unsigned long long* dbg;  // optional: 8 globaltimer stamps per (CTA, image < 2), see nfpb200_debug_phase_timing
 };
@@ -120,7 +121,7 @@ struct Lay {
   int tfull, tpart, inv, rn, wd, gp, tabs, gyraw, ggx, mhi, mlo, stg, ytab, eidx, xs, total;
   int t_fv, t_fd, t_q, t_fsrc, t_fdst, t_fptr;
   int gy_stride, x_stride, row_bytes;
-  __host__ __device__ Lay(int Cch, int nbuf, int ks) {
+  __host__ __device__ Lay(int Cch, int nbuf, int ks, int kin = 0) {
     using G = Geo<C>;
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 127) & ~127; return r; };
@@ -149,7 +150,7 @@ struct Lay {
       t_fd = tabs + Tables<C>::NF * 2;
       t_q = t_fsrc = t_fdst = t_fptr = 0;
     }
-    gy_stride = align_up(C::K * C::P * 2, 128);
+    gy_stride = align_up((C::K + kin) * C::P * 2, 128);
     gyraw = take(MODE == MODE_BWD ? nbuf * gy_stride : (MODE == MODE_POOL_BWD ? C::K * 4 : 0));
     ggx = take(MODE == MODE_POOL_BWD ? Cch * 4 : 0);
     mhi = take(BWD ? G::MT * 16 * G::MS : 0);
@@ -171,11 +172,11 @@ __global__ void __launch_bounds__(NW * 32, NW == kNWSmall ? 2 : 1) token_kernel(
   constexpr bool BWD = (MODE == MODE_BWD || MODE == MODE_POOL_BWD);
   constexpr bool POOLED = (MODE == MODE_POOL_FWD || MODE == MODE_POOL_BWD);
   constexpr int NT = NW * 32;
-  constexpr int GY_BYTES = K * P * 2;
+  const int GY_BYTES = (K + a.kin) * P * 2;  // (multi-radius launch: kin inner-radius planes in front)
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int Cch = a.C, NBUF = a.nbuf, KS = a.KS;
-  const Lay<C, MODE, NW> L(Cch, NBUF, KS);
+  const Lay<C, MODE, NW> L(Cch, NBUF, KS, a.kin);
   float* tfull = reinterpret_cast<float*>(smem_raw + L.tfull);
   float* tpart = reinterpret_cast<float*>(smem_raw + L.tpart);
   float* inv = reinterpret_cast<float*>(smem_raw + L.inv);
@@ -268,7 +269,8 @@ __global__ void __launch_bounds__(NW * 32, NW == kNWSmall ? 2 : 1) token_kernel(
       const int16_t* fptr = reinterpret_cast<const int16_t*>(smem_raw + L.t_fptr);
       float* Wd = reinterpret_cast<float*>(smem_raw + L.wd);
       float* Gp = reinterpret_cast<float*>(smem_raw + L.gp);
-      const unsigned char* g = smem_raw + L.gyraw + (POOLED ? 0 : bf * L.gy_stride);
+      const unsigned char* gin = smem_raw + L.gyraw + (POOLED ? 0 : bf * L.gy_stride);
+      const unsigned char* g = gin + a.kin * P * 2;
       if constexpr (POOLED) {
         float* gs = reinterpret_cast<float*>(smem_raw + L.ggx);
         if (a.proj_w) {
@@ -315,7 +317,16 @@ __global__ void __launch_bounds__(NW * 32, NW == kNWSmall ? 2 : 1) token_kernel(
       }
       auto Gv = [&](int flat) -> float {
         if constexpr (POOLED) return reinterpret_cast<const float*>(smem_raw + L.gyraw)[flat / P];
-        else return ldx<bf16>(g + flat * 2);
+        else {
+          float v = ldx<bf16>(g + flat * 2);
+          if constexpr (R >= 2) {
+            if (a.kin) {  // multi-radius launch: the same tap of the inner radius' map adds its gradient
+              const int n = flat / P, n1 = inner_tap(n, R, a.rin);
+              if (n1 >= 0) v += ldx<bf16>(gin + (n1 * P + flat - n * P) * 2);
+            }
+          }
+          return v;
+        }
       };
       for (int idx = tid; idx < P * KK; idx += NT) {
         const int p = idx / KK, o = idx - p * KK;
@@ -454,8 +465,18 @@ __global__ void __launch_bounds__(NW * 32, NW == kNWSmall ? 2 : 1) token_kernel(
         if constexpr (POOLED) {
           ytab[idx] = yv;
         } else {
-          if (a.y_f32) reinterpret_cast<float*>(a.y)[(size_t)b * K * P + idx] = yv;
-          else reinterpret_cast<bf16*>(a.y)[(size_t)b * K * P + idx] = __float2bfloat16_rn(yv);
+          const size_t yb = (size_t)b * (K + a.kin) * P;
+          if (a.y_f32) reinterpret_cast<float*>(a.y)[yb + a.kin * P + idx] = yv;
+          else reinterpret_cast<bf16*>(a.y)[yb + a.kin * P + idx] = __float2bfloat16_rn(yv);
+          if constexpr (R >= 2) {
+            if (a.kin) {  // multi-radius launch: the inner radius' taps are the inner taps of this window
+              const int n1 = inner_tap(idx / P, R, a.rin);
+              if (n1 >= 0) {
+                if (a.y_f32) reinterpret_cast<float*>(a.y)[yb + n1 * P + p] = yv;
+                else reinterpret_cast<bf16*>(a.y)[yb + n1 * P + p] = __float2bfloat16_rn(yv);
+              }
+            }
+          }
         }
       }
       if constexpr (POOLED) {
@@ -619,7 +640,7 @@ bool plan_try(const KParams& P, int nbuf, int budget, Plan& pl) {
   using G = Geo<C>;
   int ks = 1;
   while (ks < kMaxKS && ks * G::MT < NW && P.C % (2 * ks) == 0 && (P.C / (2 * ks)) % 16 == 0) ks *= 2;
-  Lay<C, MODE, NW> L(P.C, nbuf, ks);
+  Lay<C, MODE, NW> L(P.C, nbuf, ks, P.Kin);
   if (L.total > budget) return false;
   pl.ok = true;
   pl.nbuf = nbuf;
@@ -634,6 +655,7 @@ Plan plan_for(const KParams& P) {
   Plan pl{false, 0, 0, 0, 0, 0};
   if (P.C % 64 || P.C < 64) return pl;             // swizzle granule: 8 chunks of 8 channels
   if ((C::K * C::P * 2) % 16) return pl;           // upstream-gradient rows are fetched with 16-byte copies
+  if (P.Kin && (C::R < 2 || (P.Kin * C::P * 2) % 16)) return pl;  // multi-radius: both gradient blocks
   static const int want_two = [] { const char* e = getenv("NFPB200_TOKEN_TWO_CTAS"); return e ? atoi(e) : 1; }();
   // two 8-warp CTAs per SM (one image buffer each) when they fit and there is more than one image per SM to overlap
   if (want_two && plan_try<C, MODE, kNWSmall>(P, 1, kSmemPerSM / 2 - 1024, pl)) {
@@ -775,6 +797,7 @@ int token_run(const KParams& P, int op, const void* x, const void* gy, void* y, 
   a.xbs = P.x_batch_stride > 0 ? P.x_batch_stride : dense;
   a.gxbs = P.gx_batch_stride > 0 ? P.gx_batch_stride : dense;
   a.pad_mode = P.mode; a.similarity = P.similarity; a.eps = P.eps; a.y_f32 = P.y_f32;
+  a.kin = P.Kin; a.rin = P.rin;
   a.dbg = stream::g_debug_stamps.load(std::memory_order_relaxed);
   return token::launch(P, token_mode(op), a, ctx.stream);
 }

@@ -348,6 +348,83 @@ def nfp_head(x: torch.Tensor, weight: torch.Tensor, bias, cfg: NFPConfig):
     return out.to(torch.promote_types(x.dtype, proj_dtype))
 
 
+class _NFPMultiRadius(torch.autograd.Function):
+    """[NFP_r(x) | NFP_R(x)] along the channel axis in ONE launch each way (desc.inner_R, include/nfp_b200.h)."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, inner_R, y_f32=False, layout=0):
+        desc = _desc_for(x, cfg, layout)
+        desc.inner_R = inner_R
+        Ho, Wo = _capi.output_shape(desc)
+        y_f32 = bool(y_f32) and x.dtype == torch.bfloat16
+        if y_f32:
+            desc.path |= _capi.FLAG_Y_F32
+        k_in = (2 * inner_R + 1) ** 2 - 1
+        y = torch.empty((x.shape[0], k_in + cfg.out_channels, Ho, Wo), dtype=torch.float32 if y_f32 else x.dtype,
+                        device=x.device)
+        _trace(desc, _capi.OP_FORWARD, f"map, radii {inner_R}+{cfg.R} in one launch")
+        with torch.cuda.device(x.device):
+            rc = _capi.load().nfpb200_forward(ctypes.byref(desc), x.data_ptr(), y.data_ptr(), None, 0,
+                                              _stream(x.device))
+        _capi.check(rc, "nfpb200_forward (multi-radius)")
+        ctx.save_for_backward(x)
+        ctx.cfg, ctx.inner_R, ctx.layout = cfg, inner_R, layout
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        desc = _desc_for(x, ctx.cfg, ctx.layout)
+        desc.inner_R = ctx.inner_R
+        if _X_STABLE_HINT:
+            desc.path |= _capi.HINT_X_STABLE
+        gy = gy.to(x.dtype).contiguous()
+        if gy.data_ptr() % 16:
+            gy = gy.clone()
+        gx = _empty_like_layout(x, ctx.layout)
+        with torch.cuda.device(x.device):
+            rc = _capi.load().nfpb200_backward(ctypes.byref(desc), x.data_ptr(), gy.data_ptr(), gx.data_ptr(),
+                                               None, 0, _stream(x.device))
+        _capi.check(rc, "nfpb200_backward (multi-radius)")
+        return gx, None, None, None, None
+
+
+def multi_radius_fusable(cfgs) -> bool:
+    """Two cosine layers whose windows nest -- (inner radius r, outer radius R > r), each with padding = its radius,
+    stride 1, dilation 1 and otherwise equal options: the radius-r window is then the inner part of the radius-R
+    window (the padding rule maps an index, whatever the pad width), so one pass over x yields both maps."""
+    if len(cfgs) != 2:
+        return False
+    a, b = cfgs
+    return (a.measure == "cosine" and b.measure == "cosine" and a.R < b.R and a.padding == a.R and b.padding == b.R
+            and a.stride == b.stride == 1 and a.dilation == b.dilation == 1 and a.padding_mode == b.padding_mode
+            and a.padding_mode != "circular" and a.similarity == b.similarity and a.eps == b.eps
+            and a.path == b.path and a.path != "generic")
+
+
+def nfp_multi_radius(x: torch.Tensor, cfgs) -> torch.Tensor:
+    """``torch.cat([nfp_similarity(x, c) for c in cfgs], dim=1)`` -- what the reference's ``MultiRadiusNFPHead``
+    computes block by block (models/nfp_heads.py:80-118: R_list = (1, 2), then ``torch.cat``) -- in ONE launch each
+    way when ``multi_radius_fusable(cfgs)`` and the fused kernels cover the map: the radius-1 map costs
+    nothing beyond the radius-2 launch, and the concatenation copy disappears.  Anything else is computed layer by
+    layer and concatenated (same values)."""
+    cfgs = tuple(cfgs)
+    if x.device.type == "cuda" and x.dim() == 4 and multi_radius_fusable(cfgs):
+        inner, outer = cfgs
+        _check_geometry(x.shape[2], x.shape[3], outer)
+        xk, out_dtype, layout = _prepare(x, outer)
+        desc = _desc_for(xk, outer, layout)
+        desc.inner_R = inner.R
+        buf = ctypes.create_string_buffer(64)
+        lib = _capi.load()
+        if (lib.nfpb200_describe_path(ctypes.byref(desc), _capi.OP_FORWARD, buf, 64) == 0
+                and lib.nfpb200_describe_path(ctypes.byref(desc), _capi.OP_BACKWARD, buf, 64) == 0):
+            y = _NFPMultiRadius.apply(xk, outer, inner.R, out_dtype == torch.float32, layout)
+            return y if y.dtype == out_dtype else y.to(out_dtype)
+    return torch.cat([nfp_similarity(x, c) for c in cfgs], dim=1)
+
+
 def nfp_similarity(x: torch.Tensor, cfg: NFPConfig) -> torch.Tensor:
     """(B, C, H, W) -> (B, k*k-1, H', W') similarity map; differentiable w.r.t. ``x``."""
     if x.device.type != "cuda":
@@ -382,5 +459,5 @@ def describe(x_shape, dtype: torch.dtype, cfg: NFPConfig, op: int = _capi.OP_FOR
     return _capi.describe_path(desc, op)
 
 
-__all__ = ["NFPConfig", "nfp_similarity", "nfp_gap_pair", "nfp_head", "shape_probe", "conv_output_size", "describe",
+__all__ = ["NFPConfig", "nfp_similarity", "nfp_gap_pair", "nfp_head", "nfp_multi_radius", "multi_radius_fusable", "shape_probe", "conv_output_size", "describe",
            "replace", "math"]

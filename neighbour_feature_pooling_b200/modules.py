@@ -183,12 +183,7 @@ class nfp_pooling(nn.Module):
         """The one-pass head (nfp_gap_pair) stands in for ``self.nfp_layer(x)`` only when that call would run the
         stock operator: a subclass overriding ``forward``, a re-bound ``similarity_measure`` or forward hooks on the
         layer must see the call, as in the reference (NFP_Pooling.py:29)."""
-        layer = self.nfp_layer
-        return (type(layer) in (NFPPooling, EnhancedNFPPooling)
-                and getattr(layer.similarity_measure, "__func__", None) is NFPPooling._measure
-                and getattr(layer.similarity_measure, "__self__", None) is layer
-                and not layer._forward_hooks and not layer._forward_pre_hooks
-                and not layer._backward_hooks and not layer._backward_pre_hooks)
+        return _stock(self.nfp_layer)
 
     def forward(self, x):
         layer = self.nfp_layer
@@ -210,4 +205,71 @@ class nfp_pooling(nn.Module):
         return x_avg * x_nfp
 
 
-__all__ = ["NFPPooling", "EnhancedNFPPooling", "nfp_pooling"]
+def _stock(layer) -> bool:
+    """True when calling ``layer(x)`` runs the stock operator (no subclass ``forward``, no re-bound
+    ``similarity_measure`` or ``forward``, no hooks): only then may a fused kernel stand in for the call."""
+    return (type(layer) in (NFPPooling, EnhancedNFPPooling)
+            and "forward" not in layer.__dict__
+            and getattr(layer.similarity_measure, "__func__", None) is NFPPooling._measure
+            and getattr(layer.similarity_measure, "__self__", None) is layer
+            and not layer._forward_hooks and not layer._forward_pre_hooks
+            and not layer._backward_hooks and not layer._backward_pre_hooks)
+
+
+class MultiRadiusNFP(nn.Module):
+    """``torch.cat([NFP_R(x) for R in R_list], dim=1)`` -- the operator inside the reference's
+    ``MultiRadiusNFPHead`` (models/nfp_heads.py:86-93,111-112) -- as one module.  With ``R_list = (1, 2)`` (the
+    reference's default), cosine and ``padding = R`` both maps come out of ONE launch each way: the 3x3
+    window is the inner part of the 5x5 window, so the radius-1 map and the concatenation are free."""
+
+    def __init__(self, in_channels, R_list=(1, 2), measure="cosine", **kwargs):
+        super().__init__()
+        self.nfp_blocks = nn.ModuleList([
+            EnhancedNFPPooling(in_channels=in_channels, R=R, measure=measure, padding=R, **kwargs) for R in R_list])
+        self.out_channels = sum(b.out_channels for b in self.nfp_blocks)
+
+    def forward(self, x):
+        if x.device.type == "cuda" and all(_stock(b) for b in self.nfp_blocks):
+            return NF.nfp_multi_radius(x, [b.config for b in self.nfp_blocks])
+        return torch.cat([b(x) for b in self.nfp_blocks], dim=1)
+
+
+def fuse_multi_radius(blocks) -> bool:
+    """Make the UNMODIFIED reference ``MultiRadiusNFPHead`` (models/nfp_heads.py:80-118) run its two radii in one
+    launch: ``fuse_multi_radius(head.nfp_blocks)``.  The head evaluates ``[blk(fmap) for blk in self.nfp_blocks]`` and
+    concatenates; after this call the first block returns the complete concatenated map and the second an empty
+    ``(B, 0, H, W)`` tensor, so the head's own ``torch.cat`` reproduces the same result.  Module structure, parameters
+    and ``state_dict`` keys are untouched (only the two instances' ``forward`` attributes are bound);
+    ``unfuse_multi_radius`` restores them.  Returns False (and changes nothing) when the blocks are not two stock
+    cosine layers with nested windows (``functional.multi_radius_fusable``)."""
+    blocks = list(blocks)
+    if len(blocks) != 2 or not all(_stock(b) for b in blocks):
+        return False
+    first, second = blocks
+    cfgs = (first.config, second.config)
+    if not NF.multi_radius_fusable(cfgs):
+        return False
+
+    def fused_forward(x):
+        if x.device.type != "cuda":
+            return type(first).forward(first, x)
+        return NF.nfp_multi_radius(x, cfgs)
+
+    def empty_forward(x):
+        if x.device.type != "cuda":
+            return type(second).forward(second, x)
+        return x.new_empty((x.shape[0], 0, x.shape[2], x.shape[3]),
+                           dtype=torch.float32 if torch.is_autocast_enabled("cuda") else x.dtype)
+
+    first.forward = fused_forward
+    second.forward = empty_forward
+    return True
+
+
+def unfuse_multi_radius(blocks):
+    for b in blocks:
+        b.__dict__.pop("forward", None)
+
+
+__all__ = ["NFPPooling", "EnhancedNFPPooling", "nfp_pooling", "MultiRadiusNFP", "fuse_multi_radius",
+           "unfuse_multi_radius"]

@@ -32,9 +32,37 @@ def test_header_symbols_are_exported():
 
 
 def test_desc_struct_matches_header_layout():
-    # ABI v2: 18 x 4-byte fields, layout + reserved (2 x 4), two 8-byte batch strides; no padding
+    # ABI v3: 18 x 4-byte fields, layout + inner_R (2 x 4), two 8-byte batch strides; no padding
     assert ctypes.sizeof(_capi.Desc) == 96
-    assert _capi.Desc.layout.offset == 72 and _capi.Desc.x_batch_stride.offset == 80
+    assert _capi.Desc.layout.offset == 72 and _capi.Desc.inner_R.offset == 76 and _capi.Desc.x_batch_stride.offset == 80
+
+
+def test_multi_radius_descriptor():
+    """desc.inner_R: y / gy = [radius-r map | radius-R map]; the fused kernels' map modes or nothing."""
+    lib = _capi.load()
+    n = ctypes.c_size_t()
+
+    def d(**kw):
+        inner = kw.pop("inner_R", 1)
+        dd = _desc(**{"B": 4, "C": 64, "R": 2, "padding": 2, **kw})
+        dd.inner_R = inner
+        return dd
+    assert _capi.describe_path(d(), _capi.OP_FORWARD) == "fused/stream_7x7_r2"
+    assert _capi.describe_path(d(H=14, W=14, dtype=_capi.BF16), _capi.OP_BACKWARD) == "fused/stream_14x14_r2"
+    assert _capi.workspace_bytes(d(), _capi.OP_BACKWARD) == 0 and _capi.launch_count(d(), _capi.OP_BACKWARD) == 1
+    tok = d(dtype=_capi.BF16)
+    tok.layout = _capi.LAYOUT_NHWC
+    assert _capi.describe_path(tok, _capi.OP_BACKWARD) == "fused/token_7x7_r2"
+    # the inner radius must be smaller than R; pooled / head modes, generic and split paths do not carry it
+    for bad in (d(inner_R=2), d(inner_R=-1), d(R=1, padding=1, inner_R=1)):
+        assert lib.nfpb200_workspace_bytes(ctypes.byref(bad), _capi.OP_FORWARD, ctypes.byref(n)) == -1
+    assert lib.nfpb200_workspace_bytes(ctypes.byref(d()), _capi.OP_POOL_FORWARD, ctypes.byref(n)) == -5
+    assert lib.nfpb200_head_supported(ctypes.byref(d())) == -5
+    for path in ("generic", "split"):
+        assert lib.nfpb200_workspace_bytes(ctypes.byref(d(path=path)), _capi.OP_FORWARD, ctypes.byref(n)) == -5
+    # maps / geometries outside the fused kernels: refused (the caller launches once per radius)
+    for bad in (d(H=9, W=9), d(stride=2), d(measure="dot"), d(padding_mode="circular")):
+        assert lib.nfpb200_workspace_bytes(ctypes.byref(bad), _capi.OP_FORWARD, ctypes.byref(n)) == -5
 
 
 def test_channels_last_layout_selection():

@@ -142,6 +142,15 @@ def test_reference_heads_run_unchanged_on_the_dropin():
         assert isinstance(h.nfp, NFPPooling) and h.nfp_out_channels == 8
         mr = heads.MultiRadiusNFPHead(in_c=32, bottleneck_dim=16)
         assert mr.compress[0].in_channels == 8 + 24
+        # the head's two radii in one launch -- only the blocks' forward attributes are bound, the module
+        # tree / state_dict are untouched, and CPU shape probes still answer block by block
+        keys = list(mr.state_dict().keys())
+        assert nfpb.fuse_multi_radius(mr.nfp_blocks)
+        assert list(mr.state_dict().keys()) == keys
+        with torch.no_grad():
+            assert [b(torch.randn(1, 32, 7, 7)).shape[1] for b in mr.nfp_blocks] == [8, 24]
+        nfpb.unfuse_multi_radius(mr.nfp_blocks)
+        assert not any("forward" in b.__dict__ for b in mr.nfp_blocks)
     finally:
         sys.path.remove(REFERENCE_ROOT)
         for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:

@@ -791,3 +791,145 @@ def test_fused_head_channels_last(shape, cuda_device):
     assert rel_err(xd.grad.float().cpu(), gx_ref) < BF16_TOL
     assert rel_err(head.nfp_proj.weight.grad.cpu(), t.t() @ gap_n) < BF16_TOL
     assert rel_err(head.nfp_proj.bias.grad.cpu(), t.sum(0)) < BF16_TOL
+
+
+# ---- several radii on the same map in one launch (MultiRadiusNFPHead, models/nfp_heads.py:80-118) ---------
+MULTI_SHAPES = [(5, 64, 7, 7), (3, 512, 7, 7), (2, 64, 14, 14), (2, 256, 14, 14), (300, 16, 7, 7)]
+
+
+def _multi_ref(x, g, mode, similarity):
+    """cat([NFP_1(x), NFP_2(x)], dim=1) and its input gradient from the oracle, layer by layer as the reference does."""
+    kw1 = dict(R=1, measure="cosine", padding=1, padding_mode=mode, similarity=similarity)
+    kw2 = dict(R=2, measure="cosine", padding=2, padding_mode=mode, similarity=similarity)
+    y1, gx1 = O.nfp_forward_backward(x.double(), g[:, :8].double().contiguous(), **kw1)
+    y2, gx2 = O.nfp_forward_backward(x.double(), g[:, 8:].double().contiguous(), **kw2)
+    y1, y2, gx1, gx2 = (torch.as_tensor(np.asarray(t)) for t in (y1, y2, gx1, gx2))
+    return torch.cat([y1, y2], dim=1), gx1 + gx2
+
+
+@pytest.mark.parametrize("shape", MULTI_SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("mode,similarity", [("reflect", True), ("zeros", False), ("replicate", True)],
+                         ids=["reflect", "zeros_dist", "replicate"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_multi_radius_one_launch_vs_oracle(shape, mode, similarity, dtype, cuda_device):
+    """R = 1 and R = 2 on the same map from ONE forward and ONE backward launch (desc.inner_R): the 3x3 window is the
+    inner part of the 5x5 window under every padding rule, so the result must equal the reference's block-by-block
+    evaluation + torch.cat, and the gradient the sum of the two layers' gradients."""
+    B, C, H, W = shape
+    gen = torch.Generator().manual_seed(B * 31 + C + H)
+    x = torch.randn(B, C, H, W, generator=gen)
+    if C % 128 == 0:
+        x = x.relu()
+    x[0, :, 0, 0] = 0.0
+    x[-1, :, H - 1, W - 1] *= 1e-9
+    g = torch.randn(B, 32, H, W, generator=gen)
+    if dtype == torch.bfloat16:
+        x, g = x.bfloat16().float(), g.bfloat16().float()
+    blocks = nfpb.MultiRadiusNFP(C, padding_mode=mode, similarity=similarity).to(cuda_device)
+    cfgs = [b.config for b in blocks.nfp_blocks]
+    assert NF.multi_radius_fusable(cfgs)
+    sl = slice(B - 4, B) if B > 32 else slice(0, B)
+    y_ref, gx_ref = _multi_ref(x[sl], g[sl], mode, similarity)
+    NF.PATH_TRACE = set()
+    try:
+        xd = x.to(cuda_device, dtype).requires_grad_(True)
+        y = blocks(xd)
+        y.backward(g.to(cuda_device, dtype))
+        trace = set(NF.PATH_TRACE)
+    finally:
+        NF.PATH_TRACE = None
+    assert any("radii 1+2 in one launch" in t and "fused/stream" in t for t in trace), trace
+    assert y.shape == (B, 32, H, W)
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert rel_err(y.detach().float().cpu()[sl], y_ref) < tol
+    assert rel_err(xd.grad.float().cpu()[sl], gx_ref) < tol
+    # against the same kernels launched once per radius (+ cat): the forward values are the same table entries
+    x2 = x.to(cuda_device, dtype).requires_grad_(True)
+    y2 = torch.cat([b(x2) for b in blocks.nfp_blocks], dim=1)
+    y2.backward(g.to(cuda_device, dtype))
+    assert rel_err(y.detach().float().cpu(), y2.detach().float().cpu()) < (2e-6 if dtype == torch.float32 else 1e-2)
+    assert rel_err(xd.grad.float().cpu(), x2.grad.float().cpu()) < (1e-5 if dtype == torch.float32 else 2e-2)
+    # bit-repeatable
+    x3 = x.to(cuda_device, dtype).requires_grad_(True)
+    y3 = blocks(x3)
+    y3.backward(g.to(cuda_device, dtype))
+    assert torch.equal(y3, y) and torch.equal(x3.grad, xd.grad)
+
+
+@pytest.mark.parametrize("shape", [(5, 64, 7, 7), (3, 512, 7, 7), (2, 64, 14, 14), (200, 64, 7, 7)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("autocast", [False, True], ids=["plain", "autocast"])
+def test_multi_radius_channels_last(shape, autocast, cuda_device):
+    """The same on a channels_last bf16 map: the tensor-core token kernels, one launch each way, gradient back in
+    channels_last; under autocast the map is fp32 (F.cosine_similarity is on autocast's fp32 list)."""
+    B, C, H, W = shape
+    gen = torch.Generator().manual_seed(B * 13 + C + H)
+    x = torch.randn(B, C, H, W, generator=gen).bfloat16().float()
+    g = torch.randn(B, 32, H, W, generator=gen).bfloat16().float()
+    sl = slice(B - 4, B) if B > 32 else slice(0, B)
+    y_ref, gx_ref = _multi_ref(x[sl], g[sl], "reflect", True)
+    blocks = nfpb.MultiRadiusNFP(C).to(cuda_device)
+    xd = x.to(cuda_device, torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    NF.PATH_TRACE = set()
+    try:
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            y = blocks(xd)
+        y.backward(g.to(cuda_device, y.dtype))
+        trace = set(NF.PATH_TRACE)
+    finally:
+        NF.PATH_TRACE = None
+    assert any("radii 1+2 in one launch" in t and "fused/token" in t and "channels-last" in t for t in trace), trace
+    assert y.dtype == (torch.float32 if autocast else torch.bfloat16) and y.shape == (B, 32, H, W)
+    assert xd.grad.stride() == xd.stride(), "gradient comes back channels_last"
+    assert rel_err(y.detach().float().cpu()[sl], y_ref) < BF16_TOL
+    assert rel_err(xd.grad.float().cpu()[sl], gx_ref) < BF16_TOL
+
+
+def test_multi_radius_fallbacks_and_head_fusion(cuda_device):
+    """(a) configurations the one-launch form does not cover are computed layer by layer + cat (same values);
+    (b) fuse_multi_radius() on a ModuleList built exactly like MultiRadiusNFPHead.nfp_blocks (nfp_heads.py:86-93): the
+    head's own `torch.cat([blk(fmap) for blk in self.nfp_blocks], dim=1)` then runs one launch each way."""
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 24, 9, 11, generator=gen)          # a map no fused kernel covers
+    g = torch.randn(3, 32, 9, 11, generator=gen)
+    y_ref, gx_ref = _multi_ref(x, g, "reflect", True)
+    mr = nfpb.MultiRadiusNFP(24).to(cuda_device)
+    xd = x.to(cuda_device).requires_grad_(True)
+    y = mr(xd)
+    y.backward(g.to(cuda_device))
+    assert rel_err(y.detach().cpu(), y_ref) < FP32_TOL and rel_err(xd.grad.cpu(), gx_ref) < FP32_TOL
+    # a non-nested / non-cosine list is never fused
+    assert not NF.multi_radius_fusable([nfpb.NFPPooling(8, R=2, measure="cosine", padding=2).config,
+                                        nfpb.NFPPooling(8, R=1, measure="cosine", padding=1).config])
+    assert not NF.multi_radius_fusable([nfpb.NFPPooling(8, R=1, measure="dot", padding=1).config,
+                                        nfpb.NFPPooling(8, R=2, measure="dot", padding=2).config])
+    # (b)
+    x = torch.randn(4, 64, 7, 7, generator=gen)
+    g = torch.randn(4, 32, 7, 7, generator=gen)
+    y_ref, gx_ref = _multi_ref(x, g, "reflect", True)
+    blocks = torch.nn.ModuleList([nfpb.EnhancedNFPPooling(in_channels=64, R=R, measure="cosine", padding=R)
+                                  for R in (1, 2)]).to(cuda_device)
+    keys = list(blocks.state_dict().keys())
+
+    def head_cat(fmap):   # the two lines of MultiRadiusNFPHead.forward that touch the blocks (nfp_heads.py:111-112)
+        nfp_maps = [blk(fmap) for blk in blocks]
+        return torch.cat(nfp_maps, dim=1)
+
+    assert nfpb.fuse_multi_radius(blocks)
+    assert list(blocks.state_dict().keys()) == keys
+    NF.PATH_TRACE = set()
+    try:
+        xd = x.to(cuda_device).requires_grad_(True)
+        y = head_cat(xd)
+        y.backward(g.to(cuda_device))
+        trace = set(NF.PATH_TRACE)
+    finally:
+        NF.PATH_TRACE = None
+    assert len(trace) == 1 and "radii 1+2 in one launch" in next(iter(trace)), trace
+    assert rel_err(y.detach().cpu(), y_ref) < FP32_TOL and rel_err(xd.grad.cpu(), gx_ref) < FP32_TOL
+    nfpb.unfuse_multi_radius(blocks)
+    assert blocks[1](x.to(cuda_device)).shape == (4, 24, 7, 7)
+    # a customised block (hook) is left alone
+    h = blocks[0].register_forward_hook(lambda m, i, o: o)
+    assert not nfpb.fuse_multi_radius(blocks)
+    h.remove()
