@@ -164,22 +164,24 @@ class ClockSampler:
 class LayerBench:
     """Rotating device buffers + C-ABI launches for one (shape, R, dtype) configuration."""
 
-    def __init__(self, dev, B, C, H, W, R, dtype_name, seed=0, layout="nchw"):
+    def __init__(self, dev, B, C, H, W, R, dtype_name, seed=0, layout="nchw", inner_R=0):
         from neighbour_feature_pooling_b200 import _capi
         self.capi = _capi
         self.lib = _capi.load()
         self.dev = dev
         self.B, self.C, self.H, self.W, self.R = B, C, H, W, R
-        self.K = (2 * R + 1) ** 2 - 1
+        # inner_R > 0: the multi-radius launch (SURVEY 8 f3) -- y / gy carry the radius-inner_R map in front
+        self.K = (2 * R + 1) ** 2 - 1 + ((2 * inner_R + 1) ** 2 - 1 if inner_R else 0)
         self.tdtype = torch.float32 if dtype_name == "fp32" else torch.bfloat16
         self.esz = 4 if dtype_name == "fp32" else 2
         lay = _capi.LAYOUT_NHWC if layout == "nhwc" else _capi.LAYOUT_NCHW   # nhwc: channels_last x / grad_x, in place
         self.layout = layout
         self.desc = _capi.make_desc(_capi.F32 if dtype_name == "fp32" else _capi.BF16, B, C, H, W, R, 1, R, 1,
-                                    "reflect", "cosine", True, False, 1e-6, 1, 1e-6, "auto", layout=lay)
+                                    "reflect", "cosine", True, False, 1e-6, 1, 1e-6, "auto", layout=lay, inner_R=inner_R)
         # backward entry points: x is a saved activation, not an output of the preceding launch (what autograd passes)
         self.desc_bwd = _capi.make_desc(_capi.F32 if dtype_name == "fp32" else _capi.BF16, B, C, H, W, R, 1, R, 1,
-                                        "reflect", "cosine", True, False, 1e-6, 1, 1e-6, "auto", layout=lay)
+                                        "reflect", "cosine", True, False, 1e-6, 1, 1e-6, "auto", layout=lay,
+                                        inner_R=inner_R)
         if os.environ.get("NFPB200_BENCH_NO_HINT", "0") != "1":
             self.desc_bwd.path |= _capi.HINT_X_STABLE
         self.path_fwd = _capi.describe_path(self.desc, _capi.OP_FORWARD)
@@ -686,6 +688,23 @@ def main():
                                   "path": s.path_bwd})
                     del s
                     torch.cuda.empty_cache()
+    # ---- R = 1 and R = 2 on the same map (MultiRadiusNFPHead, models/nfp_heads.py:80-118) in ONE launch each
+    # way (desc.inner_R) against the same kernels launched once per radius (the concatenation copies not even counted)
+    multi = []
+    if not args.no_sweep and rank == 0:
+        by_name = {e["workload"]: e for e in sweep}
+        for shp, dt, lay in (("l4", "fp32", "nchw"), ("l4", "bf16", "nhwc"), ("l3", "fp32", "nchw")):
+            c, h, w, _ = SHAPES[shp]
+            s = LayerBench(dev, B, c, h, w, 2, dt, layout=lay, inner_R=1)
+            n = max(min(args.steps, 200), 60)
+            tt = s.timed(s.step, n, 5, sampler, "sweep") / n
+            sfx = " channels-last" if lay == "nhwc" else ""
+            sep = [by_name.get(workload_name(B, c, h, w, r, dt) + sfx) for r in (1, 2)]
+            multi.append({"workload": f"nfp_cosine_fwd_bwd B={B} {c}x{h}x{w} 3x3 + 5x5 maps (32 channels) {dt}{sfx}",
+                          "us_per_step_one_launch": tt * 1e6, "path": s.path_bwd,
+                          "us_per_step_launch_per_radius": (sep[0]["us_per_step"] + sep[1]["us_per_step"]) if all(sep) else None})
+            del s
+            torch.cuda.empty_cache()
     # ---- metric part (ii): ResNet18 + NFP training images/s (DDP over NCCL when N > 1) ---------------------------
     train = None
     if not args.no_train:
@@ -772,6 +791,8 @@ def main():
         line["pooled"] = pooled
         if sweep:
             line["sweep"] = sweep
+        if multi:
+            line["multi_radius"] = multi
         if train is not None:
             line["train"] = train
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
