@@ -87,7 +87,7 @@ int choose_path(const nfpb200_desc_t* d, const KParams& P, int op) {
 }
 
 size_t path_workspace_bytes(int path, const nfpb200_desc_t* d, const KParams& P, int op) {
-  if (path == 3) return planar_workspace_bytes(P, op);
+  if (path == 3) return planar_workspace_bytes(P, d->dtype, op);
   if (path == 4) return 0;
   return path ? 0 : generic_workspace_bytes(P, d->dtype, d->measure, op);
 }
@@ -172,7 +172,7 @@ int nfpb200_launch_count(const nfpb200_desc_t* desc, int32_t op, int32_t* launch
   if (!launches || op < NFPB200_OP_FORWARD || op > NFPB200_OP_POOL_BACKWARD) return NFPB200_EINVAL;
   int path = choose_path(desc, P, op);
   if (path < 0) return path;
-  *launches = path == 4 ? 1 : path == 3 ? planar_launch_count(op) : (path ? 1 : generic_launch_count(P, desc->dtype, desc->measure, op));
+  *launches = path == 4 ? 1 : path == 3 ? planar_launch_count(P, desc->dtype, op) : (path ? 1 : generic_launch_count(P, desc->dtype, desc->measure, op));
   return NFPB200_OK;
 }
 

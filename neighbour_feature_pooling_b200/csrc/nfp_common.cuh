@@ -116,8 +116,8 @@ int token_head_run(const KParams& P, int op, const void* x, const float* proj_w,
 
 // planar kernels (cosine, stride 1, dilation 1, pad = R, any map size; map mode only): nfp_planar.cu
 bool planar_supported(const KParams& P, int dtype, int measure, int op);
-size_t planar_workspace_bytes(const KParams& P, int op);
-int planar_launch_count(int op);
+size_t planar_workspace_bytes(const KParams& P, int dtype, int op);
+int planar_launch_count(const KParams& P, int dtype, int op);
 const char* planar_name(const KParams& P, int dtype, int op);
 int planar_forward(const KParams& P, int dtype, const void* x, void* y, const LaunchCtx& ctx);
 int planar_backward(const KParams& P, int dtype, const void* x, const void* gy, void* gx, const LaunchCtx& ctx);

@@ -1,28 +1,25 @@
 // Planar NFP kernels for sm_100a: cosine measure, stride 1, dilation 1, padding = R, ANY map size and channel
 // count -- the shapes the streaming fused kernels (nfp_stream_impl.cuh) do not cover, in particular the large,
 // shallow maps of the reference's multi-stage heads (models/texture_pooling.py:211-268: 16x112x112, 24x56x56,
-// 40x28x28 ...).  The per-image tables do not fit in shared memory there, so the passes are separate launches that
-// exchange small per-pixel tables through a caller-provided workspace; every access is coalesced along the plane
-// (thread = pixel), neighbour re-reads are served by L1/L2, and -- unlike the generic scatter kernels -- nothing uses
-// atomics, so the results are bit-reproducible:
+// 40x28x28 ...).  An image's tables do not fit in shared memory there, so the work is cut into ROW BANDS instead of
+// images.  Thread = pixel, every access coalesced along the plane, gather form throughout: no atomics,
+// bit-reproducible.  Two forms:
 //
-//   table    T[b][v][p]   v = 0: |x_p|^2,  v = 1..K/2: dot(x_p, x_q) for the "forward" window neighbours q,
-//                         v = K/2+1: 1 / max(|x_p|, eps)
-//   forward  y[b][n][p]   = dot(p, v_n) / (max(|p|,eps) max(|v_n|,eps)),  v_n = padded tap n of p      (nfp.py:150-159)
-//   coef     Wd[b][o][p]  the k x k stencil of ATen's cosine_similarity backward, gather form
-//   apply    gx[b][c][p]  = sum_o Wd[o][p] * x[c][p + off(o)]
-//
-// Forward = table + forward (2 launches); backward = table + coef + apply (3 launches, x re-read from L2).
+//   band    ("planar/band", planes and row groups 16-byte aligned) ONE launch each way, no workspace: a CTA owns TH map
+//           rows of one image and fetches them plus R halo rows of EVERY channel with TMA bulk copies (cp.async.bulk,
+//           one per channel: the rows of a plane are contiguous) onto one mbarrier; inverse norms of the slab's pixels,
+//           the dots of every band pixel with its whole window, the forward values or the k x k stencil coefficients
+//           (closed form of ATen's cosine_similarity backward) and the stencil application all run out of
+//           that slab -- x is read from HBM once per launch, the per-pixel tables / coefficient planes never exist.
+//   scalar  ("planar/table", any shape) separate launches exchanging per-pixel tables through the caller's workspace:
+//             table    T[b][v][p]   v = 0: |x_p|^2,  v = 1..K/2: dot(x_p, x_q) for the "forward" window neighbours q,
+//                                   v = K/2+1: 1 / max(|x_p|, eps)
+//             forward  y[b][n][p]   = dot(p, v_n) / (max(|p|,eps) max(|v_n|,eps)),  v_n = padded tap n of p (nfp.py:150-159)
+//             coef     Wd[b][o][p]  the k x k stencil of the backward, gather form
+//             apply    gx[b][c][p]  = sum_o Wd[o][p] * x[c][p + off(o)]
+//           forward = table + forward (2 launches); backward = table + coef + apply (3 launches, x re-read from L2).
 // The window radius is a template parameter: all tap / offset loops are unrolled and the per-thread arrays live in
 // registers.
-//
-// The two passes that stream x (table, apply) exist in two forms:
-//   band    a CTA owns a band of TH map rows of one image; one warp fetches the band (+ halo rows) of EVERY channel
-//           with TMA bulk copies (cp.async.bulk, one per channel: the rows of a plane are contiguous) onto one
-//           mbarrier, then thread = pixel runs the channel loop out of shared memory.  Needs 16-byte aligned
-//           planes and row groups ("planar/band").  ncu on the scalar form showed why: thread-serial channel
-//           loops of dependent-latency LDGs reach 1.1 TB/s (long-scoreboard stalls, 13 % of DRAM peak).
-//   scalar  thread = pixel, plain coalesced loads through L1 -- any shape ("planar/table").
 #include <stdlib.h>
 
 #include "nfp_common.cuh"
@@ -253,74 +250,24 @@ __global__ void __launch_bounds__(kThreads) planar_apply_kernel(const T* __restr
   }
 }
 
-// ---- band form: TMA-staged row bands ---------------------------------------------------------------------------
-// smem: [0,16) mbarrier, then C planes of `rows_sm` rows x W elements; image row r sits at smem row r - row_base.
+// ---- fused band kernels: the whole forward / backward of a row band in ONE launch, no workspace -------------------
+// A CTA owns TH map rows of one image and fetches them with A >= R halo rows on either side (all channels, TMA bulk
+// copies as above).  Everything a band pixel needs lives inside that slab:
+//   1. inverse clamped norms of every fetched pixel -> shared memory;
+//   2. thread = band pixel: |x_p|^2 and the dots with ALL window neighbours (both directions: dot(p,q) is computed at p
+//      and again at q, with the same operands in the same channel order, so both get identical bits);
+//   forward: y from those dots and the neighbours' inverse norms;
+//   backward: the k x k stencil coefficients in registers (closed form of ATen's backward, gather form; upstream
+//      gradients straight from global memory, coalesced along the plane), then gx = stencil(x) out of the same slab.
+// x is read from HBM once (plus the halo rows, an L2 hit), gy and gx once; the per-pixel tables / coefficient planes of
+// the three-launch form never exist.  No atomics, fixed order: bit-reproducible.
 template <typename T, int R>
-__global__ void __launch_bounds__(kThreads) planar_table_band_kernel(const T* __restrict__ x, float* __restrict__ tab,
-                                                                     PlanarParams q, int TH, int A) {
-  using Wn = Win<R>;
-  constexpr int k = Wn::k, CTR = Wn::CTR, ND = Wn::ND, ESZ = (int)sizeof(T);
-  extern __shared__ __align__(128) unsigned char sm[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm);
-  unsigned char* xs = sm + 16;
-  const int b = blockIdx.y, r0 = blockIdx.x * TH;
-  const int rows_ld = min(TH + A, q.H - r0);
-  const int pitch = (TH + A) * q.W * ESZ;  // bytes per channel plane in shared memory
-  if (threadIdx.x == 0) {
-    ptx::mbar_init(bar, 1);
-    ptx::fence_mbar_init();
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const uint32_t bytes = (uint32_t)(rows_ld * q.W * ESZ);
-    if (threadIdx.x == 0) ptx::mbar_expect_tx(bar, bytes * (uint32_t)q.C);
-    __syncwarp();
-    const T* src = x + (size_t)b * q.C * q.P + (size_t)r0 * q.W;
-    for (int c = threadIdx.x; c < q.C; c += 32) ptx::bulk_g2s(xs + (size_t)c * pitch, src + (size_t)c * q.P, bytes, bar);
-  }
-  ptx::mbar_wait(bar, 0);
-  for (int t = threadIdx.x; t < TH * q.W; t += blockDim.x) {
-    const int lr = t / q.W, pc = t - lr * q.W, pr = r0 + lr;
-    if (pr >= q.H) break;
-    int off[ND];
-    bool in[ND];
-    float acc[ND + 1];
-#pragma unroll
-    for (int d = 0; d < ND; ++d) {
-      const int o = CTR + 1 + d, dy = o / k - R, dx = o % k - R;
-      in[d] = window_pixel(pr, pc, dy, dx, q) >= 0;
-      off[d] = in[d] ? (dy * q.W + dx) * ESZ : 0;
-      acc[d + 1] = 0.f;
-    }
-    acc[0] = 0.f;
-    const unsigned char* pl = xs + t * ESZ;
-#pragma unroll(R == 1 ? 4 : (R == 2 ? 2 : 1))
-    for (int c = 0; c < q.C; ++c, pl += pitch) {
-      const float xc = ptx::ldx<T>(pl);
-      acc[0] = fmaf(xc, xc, acc[0]);
-#pragma unroll
-      for (int d = 0; d < ND; ++d) acc[d + 1] = fmaf(xc, ptx::ldx<T>(pl + off[d]), acc[d + 1]);
-    }
-    float* tb = tab + (size_t)b * Wn::NPL * q.P + (size_t)pr * q.W + pc;
-    tb[0] = acc[0];
-#pragma unroll
-    for (int d = 0; d < ND; ++d) tb[(size_t)(d + 1) * q.P] = in[d] ? acc[d + 1] : 0.f;
-    tb[(size_t)Wn::NV * q.P] = 1.f / fmaxf(sqrtf(acc[0]), q.eps);
-  }
-}
-
-template <typename T, int R>
-__global__ void __launch_bounds__(kThreads) planar_apply_band_kernel(const T* __restrict__ x,
-                                                                     const float* __restrict__ wd, T* __restrict__ gx,
-                                                                     PlanarParams q, int TH, int A) {
-  using Wn = Win<R>;
-  constexpr int k = Wn::k, KK = Wn::KK, ESZ = (int)sizeof(T);
-  extern __shared__ __align__(128) unsigned char sm[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm);
-  unsigned char* xs = sm + 16;
-  const int b = blockIdx.y, r0 = blockIdx.x * TH;
-  const int top = max(r0 - A, 0), bot = min(r0 + TH + A, q.H);   // image rows fetched
-  const int pitch = (TH + 2 * A) * q.W * ESZ;
+__device__ __forceinline__ void band_fetch(const T* __restrict__ x, unsigned char* xs, uint64_t* bar, const PlanarParams& q,
+                                           int b, int r0, int TH, int A, int& top, int& bot, int& pitch) {
+  constexpr int ESZ = (int)sizeof(T);
+  top = max(r0 - A, 0);
+  bot = min(r0 + TH + A, q.H);   // image rows fetched
+  pitch = (TH + 2 * A) * q.W * ESZ;
   if (threadIdx.x == 0) {
     ptx::mbar_init(bar, 1);
     ptx::fence_mbar_init();
@@ -335,34 +282,174 @@ __global__ void __launch_bounds__(kThreads) planar_apply_band_kernel(const T* __
     for (int c = threadIdx.x; c < q.C; c += 32) ptx::bulk_g2s(dst + (size_t)c * pitch, src + (size_t)c * q.P, bytes, bar);
   }
   ptx::mbar_wait(bar, 0);
+}
+
+// inverse clamped norm of every fetched pixel (slab rows top - (r0 - A) .. bot - (r0 - A))
+template <typename T>
+__device__ __forceinline__ void band_norms(const unsigned char* xs, float* inv, const PlanarParams& q, int r0, int A, int top,
+                                           int bot, int pitch) {
+  constexpr int ESZ = (int)sizeof(T);
+  const int first = (top - (r0 - A)) * q.W, last = (bot - (r0 - A)) * q.W;
+  for (int t = first + threadIdx.x; t < last; t += blockDim.x) {
+    const unsigned char* pl = xs + (size_t)t * ESZ;
+    float s = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < q.C; ++c, pl += pitch) {
+      const float v = ptx::ldx<T>(pl);
+      s = fmaf(v, v, s);
+    }
+    inv[t] = 1.f / fmaxf(sqrtf(s), q.eps);
+  }
+  __syncthreads();
+}
+
+// acc[o] = dot(x_p, x_{p + off(o)}) for the in-map window entries (acc[CTR] = |x_p|^2; outside: junk, never used)
+template <typename T, int R>
+__device__ __forceinline__ void band_dots(const unsigned char* pl, int pitch, int C, const int (&off)[(2 * R + 1) * (2 * R + 1)],
+                                          float (&acc)[(2 * R + 1) * (2 * R + 1)]) {
+  constexpr int KK = (2 * R + 1) * (2 * R + 1);
+#pragma unroll
+  for (int o = 0; o < KK; ++o) acc[o] = 0.f;
+#pragma unroll(R == 1 ? 4 : 2)
+  for (int c = 0; c < C; ++c, pl += pitch) {
+    const float xc = ptx::ldx<T>(pl);
+#pragma unroll
+    for (int o = 0; o < KK; ++o) acc[o] = fmaf(xc, ptx::ldx<T>(pl + off[o]), acc[o]);
+  }
+}
+
+template <typename T, int R>
+__global__ void __launch_bounds__(kThreads) planar_fused_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, PlanarParams q,
+                                                                    int TH, int A) {
+  using Wn = Win<R>;
+  constexpr int k = Wn::k, KK = Wn::KK, CTR = Wn::CTR, ESZ = (int)sizeof(T);
+  extern __shared__ __align__(128) unsigned char sm[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm);
+  unsigned char* xs = sm + 16;
+  const int b = blockIdx.y, r0 = blockIdx.x * TH;
+  int top, bot, pitch;
+  band_fetch<T, R>(x, xs, bar, q, b, r0, TH, A, top, bot, pitch);
+  float* inv = reinterpret_cast<float*>(xs + (size_t)q.C * pitch);
+  band_norms<T>(xs, inv, q, r0, A, top, bot, pitch);
   for (int t = threadIdx.x; t < TH * q.W; t += blockDim.x) {
     const int lr = t / q.W, pc = t - lr * q.W, pr = r0 + lr;
     if (pr >= q.H) break;
-    const int p = pr * q.W + pc;
-    const float* wb = wd + (size_t)b * KK * q.P + p;
+    const int p = pr * q.W + pc, ps = (lr + A) * q.W + pc;   // pixel in the map / in the slab
     int off[KK];
-    float w[KK];
+    float acc[KK];
 #pragma unroll
     for (int o = 0; o < KK; ++o) {
       const int dy = o / k - R, dx = o % k - R;
-      const bool in = window_pixel(pr, pc, dy, dx, q) >= 0;
-      off[o] = in ? (dy * q.W + dx) * ESZ : 0;   // outside the map: coefficient 0 on the pixel itself
-      w[o] = in ? wb[(size_t)o * q.P] : 0.f;
+      off[o] = window_pixel(pr, pc, dy, dx, q) >= 0 ? (dy * q.W + dx) * ESZ : 0;
     }
-    const unsigned char* pl = xs + ((size_t)(lr + A) * q.W + pc) * ESZ;
+    band_dots<T, R>(xs + (size_t)ps * ESZ, pitch, q.C, off, acc);
+    const float ip = inv[ps];
+    T* yb = y + (size_t)b * Wn::K * q.P + p;
+    const bool interior = pr >= R && pr < q.H - R && pc >= R && pc < q.W - R;
+#pragma unroll
+    for (int tp = 0; tp < KK; ++tp) {
+      if (tp == CTR) continue;
+      const int dy = tp / k - R, dx = tp % k - R;
+      float yv = 0.f;
+      if (interior) {
+        yv = acc[tp] * (ip * inv[ps + dy * q.W + dx]);
+      } else {
+        int o;
+        const int v = tap_landing<R>(pr, pc, dy, dx, q, o);
+        if (v >= 0) {
+          float d = 0.f;   // acc[o] with a run-time o: select (the array must stay in registers)
+#pragma unroll
+          for (int oo = 0; oo < KK; ++oo) d = (oo == o) ? acc[oo] : d;
+          yv = d * (ip * inv[ps + (v - p)]);
+        }
+      }
+      if (!q.similarity) yv = 1.f - yv;
+      yb[(size_t)(tp < CTR ? tp : tp - 1) * q.P] = from_f32<T>(yv);
+    }
+  }
+}
+
+template <typename T, int R>
+__global__ void __launch_bounds__(kThreads) planar_fused_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy,
+                                                                    T* __restrict__ gx, PlanarParams q, int TH, int A) {
+  using Wn = Win<R>;
+  constexpr int k = Wn::k, KK = Wn::KK, K = Wn::K, CTR = Wn::CTR, ESZ = (int)sizeof(T);
+  extern __shared__ __align__(128) unsigned char sm[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm);
+  unsigned char* xs = sm + 16;
+  const int b = blockIdx.y, r0 = blockIdx.x * TH;
+  int top, bot, pitch;
+  band_fetch<T, R>(x, xs, bar, q, b, r0, TH, A, top, bot, pitch);
+  float* inv = reinterpret_cast<float*>(xs + (size_t)q.C * pitch);
+  band_norms<T>(xs, inv, q, r0, A, top, bot, pitch);
+  const float sgn = q.similarity ? 1.f : -1.f;
+  const T* gyb = gy + (size_t)b * K * q.P;
+  for (int t = threadIdx.x; t < TH * q.W; t += blockDim.x) {
+    const int lr = t / q.W, pc = t - lr * q.W, pr = r0 + lr;
+    if (pr >= q.H) break;
+    const int p = pr * q.W + pc, ps = (lr + A) * q.W + pc;
+    int off[KK];
+    float acc[KK], w[KK];
+#pragma unroll
+    for (int o = 0; o < KK; ++o) {
+      const int dy = o / k - R, dx = o % k - R;
+      off[o] = window_pixel(pr, pc, dy, dx, q) >= 0 ? (dy * q.W + dx) * ESZ : 0;
+    }
+    const unsigned char* pl0 = xs + (size_t)ps * ESZ;
+    band_dots<T, R>(pl0, pitch, q.C, off, acc);
+    const float t0 = acc[CTR], ip = inv[ps];
+    const float nrm = sqrtf(t0);
+    const float rnp = nrm > 0.f ? ip / nrm : 0.f;  // 1 / (N_p |x_p|): the norm term of ATen's backward, 0 at x = 0
+    const bool interior = pr >= 2 * R && pr < q.H - 2 * R && pc >= 2 * R && pc < q.W - 2 * R;
+    float s_dot = 0.f, sw = 0.f;
+    if (interior) {
+#pragma unroll
+      for (int o = 0; o < KK; ++o) {
+        if (o == CTR) continue;
+        const int dv = (o / k - R) * q.W + (o % k - R);
+        const int n = o < CTR ? o : o - 1;  // the direct tap of p towards v, and v's direct tap back
+        const float s = to_f32(gyb[(size_t)n * q.P + p]) + to_f32(gyb[(size_t)(K - 1 - n) * q.P + p + dv]);
+        w[o] = sgn * s * ip * inv[ps + dv];
+        s_dot = fmaf(w[o], acc[o], s_dot);
+      }
+    } else {
+      int FY[k][k], FX[k][k];
+#pragma unroll
+      for (int d = 0; d < k; ++d) {
+        fold_map<R>(pr + d - R, q.H, q.mode, FY[d]);
+        fold_map<R>(pc + d - R, q.W, q.mode, FX[d]);
+      }
+#pragma unroll
+      for (int o = 0; o < KK; ++o) {
+        if (o == CTR) continue;
+        const int oy = o / k, ox = o % k;
+        const int v = window_pixel(pr, pc, oy - R, ox - R, q);
+        w[o] = 0.f;
+        if (v >= 0) {
+          const float s = folded_taps<T, R>(gyb + p, FY[R], FX[R], oy, ox, q.P) +
+                          folded_taps<T, R>(gyb + v, FY[oy], FX[ox], k - 1 - oy, k - 1 - ox, q.P);
+          w[o] = sgn * s * ip * inv[ps + (v - p)];
+          s_dot = fmaf(w[o], acc[o], s_dot);
+        }
+      }
+      // taps of p that land on p itself (replicate padding): y = <p,p>/(N N), gradient 2 G (1/N^2 - y/(N |p|)) x_p
+      sw = 2.f * sgn * folded_taps<T, R>(gyb + p, FY[R], FX[R], R, R, q.P) * ip * ip;
+    }
+    w[CTR] = sw - rnp * (s_dot + sw * t0);
+    const unsigned char* pl = pl0;
     T* gp = gx + (size_t)b * q.C * q.P + p;
 #pragma unroll(R == 1 ? 4 : 1)
     for (int c = 0; c < q.C; ++c, pl += pitch, gp += q.P) {
-      float acc = 0.f;
+      float a = 0.f;
 #pragma unroll
-      for (int o = 0; o < KK; ++o) acc = fmaf(w[o], ptx::ldx<T>(pl + off[o]), acc);
-      gp[0] = from_f32<T>(acc);
+      for (int o = 0; o < KK; ++o) a = fmaf(w[o], ptx::ldx<T>(pl + off[o]), a);
+      gp[0] = from_f32<T>(a);
     }
   }
 }
 
 // Band geometry: TH rows per CTA (a multiple of the row granule g that keeps every bulk copy 16-byte aligned and
-// sized), A >= R halo rows (a multiple of g).  ok = false: this shape takes the scalar kernels.
+// sized), A >= R halo rows (a multiple of g).  ok = false: this shape takes the scalar three-launch kernels.
 struct BandPlan {
   bool ok;
   int TH, A, threads;
@@ -372,21 +459,27 @@ constexpr size_t kBandSmemMax = 100 * 1024;  // two CTAs per SM
 
 inline int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
-BandPlan band_plan(const KParams& P, int esz, bool apply) {
+// Fused band kernels: halo rows on both sides plus the inverse-norm slab; taller bands than the three-launch form (the
+// halo rows are re-read and their norms recomputed by the neighbouring CTAs: (TH + 2A) / TH of the work)
+BandPlan fused_plan(const KParams& P, int esz) {
   BandPlan bp{false, 0, 0, 0, 0};
-  static const bool off = [] { const char* e = getenv("NFPB200_PLANAR_SCALAR"); return e && e[0] == '1'; }();
+  static const bool off = [] {
+    const char* e = getenv("NFPB200_PLANAR_SCALAR");
+    return e && e[0] == '1';
+  }();
   if (off) return bp;
   const int rowB = P.W * esz;
   if (((size_t)P.H * rowB) % 16) return bp;  // every channel plane must start 16-byte aligned
   const int g = 16 / gcd_i(16, rowB);
   const int A = (P.R + g - 1) / g * g;
   const int Hg = (P.H + g - 1) / g * g;
-  int TH = ((256 + P.W - 1) / P.W + g - 1) / g * g;  // ~256 pixels per CTA ...
+  auto bytes = [&](int th) { return (size_t)P.C * (th + 2 * A) * rowB + 16 + (size_t)(th + 2 * A) * P.W * sizeof(float); };
+  static const int th_cap = [] { const char* e = getenv("NFPB200_PLANAR_TH"); return e ? atoi(e) : 8; }();
+  int TH = (th_cap + g - 1) / g * g;
   if (TH > Hg) TH = Hg;
-  while (TH > g && (long)((P.H + TH - 1) / TH) * P.B < 4 * 148) TH -= g;  // ... but enough CTAs to fill the GPU
-  auto bytes = [&](int th) { return (size_t)P.C * (th + (apply ? 2 * A : A)) * rowB + 16; };
   while (TH > g && bytes(TH) > kBandSmemMax) TH -= g;
   if (bytes(TH) > kBandSmemMax) return bp;
+  while (TH - g >= 4 * A && (long)((P.H + TH - 1) / TH) * P.B < 3 * 148) TH -= g;  // enough CTAs, bounded halo overhead
   if ((size_t)P.C * (TH + 2 * A) * rowB >= (1u << 20)) return bp;  // mbarrier transaction-count range
   bp.ok = true;
   bp.TH = TH;
@@ -414,22 +507,23 @@ size_t coef_bytes(const KParams& P) { return align256((size_t)P.B * P.k * P.k * 
 
 template <typename T, int R>
 int launch_table(const KParams& P, const PlanarParams& q, const T* x, float* tab, cudaStream_t st) {
-  const BandPlan bp = band_plan(P, (int)sizeof(T), false);
-  if (bp.ok) {
-    auto kern = planar_table_band_kernel<T, R>;
-    if (cudaError_t e = allow_smem(kern, bp.smem)) return (int)e;
-    const dim3 bgrid((unsigned)((q.H + bp.TH - 1) / bp.TH), (unsigned)q.B);
-    kern<<<bgrid, bp.threads, bp.smem, st>>>(x, tab, q, bp.TH, bp.A);
-  } else {
-    const dim3 grid((unsigned)((q.P + kThreads - 1) / kThreads), (unsigned)q.B);
-    planar_table_kernel<T, R><<<grid, kThreads, 0, st>>>(x, tab, q);
-  }
+  (void)P;
+  const dim3 grid((unsigned)((q.P + kThreads - 1) / kThreads), (unsigned)q.B);
+  planar_table_kernel<T, R><<<grid, kThreads, 0, st>>>(x, tab, q);
   return 0;
 }
 
 template <typename T, int R>
 int forward_r(const KParams& P, const T* x, T* y, const LaunchCtx& ctx) {
   const PlanarParams q = make(P);
+  const BandPlan fp = fused_plan(P, (int)sizeof(T));
+  if (fp.ok) {  // one launch, no workspace
+    auto kern = planar_fused_fwd_kernel<T, R>;
+    if (cudaError_t e = allow_smem(kern, fp.smem)) return (int)e;
+    const dim3 bgrid((unsigned)((q.H + fp.TH - 1) / fp.TH), (unsigned)q.B);
+    kern<<<bgrid, fp.threads, fp.smem, ctx.stream>>>(x, y, q, fp.TH, fp.A);
+    return (int)cudaGetLastError();
+  }
   float* tab = reinterpret_cast<float*>(ctx.ws);
   const dim3 grid((unsigned)((q.P + kThreads - 1) / kThreads), (unsigned)q.B);
   if (int rc = launch_table<T, R>(P, q, x, tab, ctx.stream)) return rc;
@@ -439,20 +533,20 @@ int forward_r(const KParams& P, const T* x, T* y, const LaunchCtx& ctx) {
 template <typename T, int R>
 int backward_r(const KParams& P, const T* x, const T* gy, T* gx, const LaunchCtx& ctx) {
   const PlanarParams q = make(P);
+  const BandPlan fp = fused_plan(P, (int)sizeof(T));
+  if (fp.ok) {  // one launch, no workspace
+    auto kern = planar_fused_bwd_kernel<T, R>;
+    if (cudaError_t e = allow_smem(kern, fp.smem)) return (int)e;
+    const dim3 bgrid((unsigned)((q.H + fp.TH - 1) / fp.TH), (unsigned)q.B);
+    kern<<<bgrid, fp.threads, fp.smem, ctx.stream>>>(x, gy, gx, q, fp.TH, fp.A);
+    return (int)cudaGetLastError();
+  }
   float* tab = reinterpret_cast<float*>(ctx.ws);
   float* wd = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx.ws) + table_bytes(P));
   const dim3 grid((unsigned)((q.P + kThreads - 1) / kThreads), (unsigned)q.B);
   if (int rc = launch_table<T, R>(P, q, x, tab, ctx.stream)) return rc;
   planar_coef_kernel<T, R><<<grid, kThreads, 0, ctx.stream>>>(tab, gy, wd, q);
-  const BandPlan bp = band_plan(P, (int)sizeof(T), true);
-  if (bp.ok) {
-    auto kern = planar_apply_band_kernel<T, R>;
-    if (cudaError_t e = allow_smem(kern, bp.smem)) return (int)e;
-    const dim3 bgrid((unsigned)((q.H + bp.TH - 1) / bp.TH), (unsigned)q.B);
-    kern<<<bgrid, bp.threads, bp.smem, ctx.stream>>>(x, wd, gx, q, bp.TH, bp.A);
-  } else {
-    planar_apply_kernel<T, R><<<grid, kThreads, 0, ctx.stream>>>(x, wd, gx, q);
-  }
+  planar_apply_kernel<T, R><<<grid, kThreads, 0, ctx.stream>>>(x, wd, gx, q);
   return (int)cudaGetLastError();
 }
 template <typename T>
@@ -480,13 +574,18 @@ bool planar_supported(const KParams& P, int dtype, int measure, int op) {
   return measure == NFPB200_COSINE && P.stride == 1 && P.dil == 1 && P.pad == P.R && P.R <= kMaxR &&
          P.mode != NFPB200_PAD_CIRCULAR && P.B <= 65535;
 }
-size_t planar_workspace_bytes(const KParams& P, int op) {
+size_t planar_workspace_bytes(const KParams& P, int dtype, int op) {
+  if (fused_plan(P, dtype == NFPB200_BF16 ? 2 : 4).ok) return 0;
   return op == NFPB200_OP_FORWARD ? table_bytes(P) : table_bytes(P) + coef_bytes(P);
 }
-int planar_launch_count(int op) { return op == NFPB200_OP_FORWARD ? 2 : 3; }
+int planar_launch_count(const KParams& P, int dtype, int op) {
+  if (fused_plan(P, dtype == NFPB200_BF16 ? 2 : 4).ok) return 1;
+  return op == NFPB200_OP_FORWARD ? 2 : 3;
+}
 const char* planar_name(const KParams& P, int dtype, int op) {
   const int esz = dtype == NFPB200_BF16 ? 2 : 4;
-  return band_plan(P, esz, op == NFPB200_OP_BACKWARD).ok ? "planar/band" : "planar/table";
+  (void)op;
+  return fused_plan(P, esz).ok ? "planar/band" : "planar/table";
 }
 
 int planar_forward(const KParams& P, int dtype, const void* x, void* y, const LaunchCtx& ctx) {

@@ -129,15 +129,19 @@ def test_path_selection_and_workspace():
     forced = _desc(B=4, C=8, H=9, W=9, stride=2, path="fused")
     n = ctypes.c_size_t()
     assert _capi.load().nfpb200_workspace_bytes(ctypes.byref(forced), _capi.OP_FORWARD, ctypes.byref(n)) == -5
-    # maps outside the streaming kernels' shape list (multi-stage heads): planar kernels, table + coefficient workspace
+    # maps outside the streaming kernels' shape list (multi-stage heads): planar kernels.  Aligned planes: fused row-band
+    # kernels, ONE launch each way and no workspace; otherwise table / coefficient passes through the caller's workspace
     planar = _desc(B=2, C=16, H=112, W=112)
     assert _capi.describe_path(planar, _capi.OP_FORWARD) == "planar/band"
     assert _capi.describe_path(planar, _capi.OP_BACKWARD) == "planar/band"
-    assert _capi.describe_path(_desc(B=2, C=7, H=9, W=13), _capi.OP_BACKWARD) == "planar/table"  # unaligned planes
-    P = 112 * 112
-    assert _capi.workspace_bytes(planar, _capi.OP_FORWARD) >= 2 * 5 * P * 4
-    assert _capi.workspace_bytes(planar, _capi.OP_BACKWARD) >= 2 * (5 + 9) * P * 4
-    assert _capi.launch_count(planar, _capi.OP_FORWARD) == 2 and _capi.launch_count(planar, _capi.OP_BACKWARD) == 3
+    assert _capi.workspace_bytes(planar, _capi.OP_FORWARD) == 0 and _capi.workspace_bytes(planar, _capi.OP_BACKWARD) == 0
+    assert _capi.launch_count(planar, _capi.OP_FORWARD) == 1 and _capi.launch_count(planar, _capi.OP_BACKWARD) == 1
+    scalar = _desc(B=2, C=7, H=9, W=13)   # unaligned planes
+    assert _capi.describe_path(scalar, _capi.OP_BACKWARD) == "planar/table"
+    P = 9 * 13
+    assert _capi.workspace_bytes(scalar, _capi.OP_FORWARD) >= 2 * 5 * P * 4
+    assert _capi.workspace_bytes(scalar, _capi.OP_BACKWARD) >= 2 * (5 + 9) * P * 4
+    assert _capi.launch_count(scalar, _capi.OP_FORWARD) == 2 and _capi.launch_count(scalar, _capi.OP_BACKWARD) == 3
     assert _capi.describe_path(planar, _capi.OP_POOL_FORWARD) == "generic/pairs"  # pooled mode: generic kernels
     assert _capi.describe_path(_desc(B=2, C=16, H=112, W=112, path="generic"), _capi.OP_FORWARD) == "generic/pairs"
     # the x-stable hint rides on `path` and changes neither the path choice nor the workspace; other bits are refused
