@@ -81,7 +81,13 @@ struct Smem {
   int wtab, stg, ytab;                         // inside the union
   int stg_warp;                                // staging bytes per warp (two buffers)
   int gyin, gyin_stride;                       // multi-radius backward: the inner radius' gradient block (two images in flight)
-  __host__ __device__ Smem(int CC, int nst, int Cfull, int kin = 0) {
+  // backward pass A publishes its per-warp tables in two rounds (upper half of the warps, then the lower half adds its
+  // own on top): half the table space, one more barrier -- what lets a 512x7x7 fp32 image stay resident (below)
+  static constexpr int NWT = BWD ? NW / 2 : NW;
+  // lanech: the lane-per-channel pass B is in use -> no per-warp store staging, no pads between the ring slots (it
+  // reads no halo; pass A's halo reads feed accumulators nobody uses, so they may land in the next slot);
+  // gy_bufs: upstream-gradient buffers (1 when every CTA handles a single image)
+  __host__ __device__ Smem(int CC, int nst, int Cfull, int kin = 0, int lanech = 0, int gy_bufs = 2) {
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 127) & ~127; return r; };
     // everything whose size is known at compile time comes first (so its address is a constant in the
@@ -99,29 +105,29 @@ struct Smem {
       t_fdst = t_fsrc + Tables<C>::NFS * 2;
       t_fptr = t_fdst + Tables<C>::NFS * 2;
       t_fv = t_fd = 0;
-      gyraw = take(2 * align_up(C::K * C::P * ESZ, 16));
     } else {
       t_fv = tabs;
       t_fd = tabs + Tables<C>::NF * 2;
       t_q = t_fsrc = t_fdst = t_fptr = 0;
-      gyraw = o;
     }
     uni = o;
-    wtab = take(NW * C::PNV * 4);  // one partial table per warp (its channel slots are summed by shuffles first)
+    wtab = take(NWT * C::PNV * 4);  // partial tables of the warps (their channel slots are summed by shuffles first)
     const int u1 = o;
     o = uni;
     stg_warp = 2 * align_up(2 * C::CPW * C::P * ESZ, 16);
-    stg = take(NW * stg_warp);
+    stg = take(lanech ? 0 : NW * stg_warp);
     const int u2 = BWD ? o : uni;
     o = uni;
     ytab = take(C::K * C::P * 4);
     const int u3 = (MODE == MODE_POOL_FWD) ? o : uni;
     o = u1 > u2 ? (u1 > u3 ? u1 : u3) : (u2 > u3 ? u2 : u3);
+    // (run-time sized regions from here on)
+    gyraw = BWD ? take(gy_bufs * align_up(C::K * C::P * ESZ, 16)) : o;
     // each slot: chunk bytes, then >= HALO zeroed elements (shared with the next slot's "before" halo);
-    // kLeadPad zeroed bytes in front of the first slot
-    slot_stride = align_up(CC * C::P * ESZ + C::HALO * ESZ, 128);
+    // kLeadPad zeroed bytes in front of the first slot, one pad behind the last
+    slot_stride = lanech ? align_up(CC * C::P * ESZ, 128) : align_up(CC * C::P * ESZ + C::HALO * ESZ, 128);
     lead = take(kLeadPad);
-    ring = take(nst * slot_stride);
+    ring = take(nst * slot_stride + (lanech ? 128 : 0));
     ggx = take(MODE == MODE_POOL_BWD ? 2 * Cfull * 4 : 0);  // pooled backward: d out / d GAP(x) of two images in flight
     gyin_stride = align_up(kin * C::P * ESZ, 16);
     gyin = take(MODE == MODE_BWD ? 2 * gyin_stride : 0);
@@ -147,7 +153,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int nst = a.nst, NCH = a.NCH, CC = a.CC;
-  const Smem<T, C, MODE, NW> L(CC, nst, a.C, a.kin);
+  const Smem<T, C, MODE, NW> L(CC, nst, a.C, a.kin, BWD && a.lanech, a.gy_bufs);
   unsigned char* ring = smem_raw + L.ring;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
   uint64_t* empty = full + kMaxStages;
@@ -268,6 +274,10 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
     for (int s = 0; s < nst; ++s) {
       uint32_t* zp = reinterpret_cast<uint32_t*>(ring + s * L.slot_stride + chunk_bytes);
       for (int i = tid; i < pad_words; i += NT) zp[i] = 0u;
+    }
+    if (a.lanech) {  // no pads between the slots: one behind the last
+      uint32_t* zp = reinterpret_cast<uint32_t*>(ring + nst * L.slot_stride);
+      for (int i = tid; i < 32; i += NT) zp[i] = 0u;
     }
   }
   // PDL: nothing below may touch global memory the preceding grid still uses -- except, with the x-stable hint, the
@@ -549,12 +559,32 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
 #pragma unroll
             for (int v = 0; v < NV; ++v) accs[j][v] += __shfl_down_sync(0xffffffffu, accs[j][v], d);
       }
-      if (lane < NS) {
-        float* wt = wtab + warp * PNV + pos * (TW * NV);
+      constexpr int NWT = Smem<T, C, MODE, NW>::NWT;
+      if constexpr (NWT == NW) {
+        if (lane < NS) {
+          float* wt = wtab + warp * PNV + pos * (TW * NV);
 #pragma unroll
-        for (int j = 0; j < TW; ++j)
+          for (int j = 0; j < TW; ++j)
 #pragma unroll
-          for (int v = 0; v < NV; ++v) wt[j * NV + v] = accs[j][v];
+            for (int v = 0; v < NV; ++v) wt[j * NV + v] = accs[j][v];
+        }
+      } else {
+        // two rounds over half the table space: the upper warps publish, the lower warps add their own on top
+        // (each entry is touched by one lane of one warp per round: fixed order, deterministic)
+        float* wt = wtab + (warp % NWT) * PNV + pos * (TW * NV);
+        if (warp >= NWT && lane < NS) {
+#pragma unroll
+          for (int j = 0; j < TW; ++j)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) wt[j * NV + v] = accs[j][v];
+        }
+        consumer_sync<NT>();
+        if (warp < NWT && lane < NS) {
+#pragma unroll
+          for (int j = 0; j < TW; ++j)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) wt[j * NV + v] += accs[j][v];
+        }
       }
     }
     NFP_STAMP(1);  // pass A done (this warp)
@@ -569,7 +599,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
     for (int i = tid; i < PNV; i += NT) {
       float s = 0.f;
 #pragma unroll 8
-      for (int t = 0; t < NW; ++t) s += wtab[t * PNV + i];  // fixed order: deterministic
+      for (int t = 0; t < Smem<T, C, MODE, NW>::NWT; ++t) s += wtab[t * PNV + i];  // fixed order: deterministic
       tfull[i] = s;
       if (i % NV == 0) {  // |x_p|^2: the clamped inverse norm (and, backward, the 1/(N |x|) of the norm term)
         const int p = i / NV;
@@ -989,7 +1019,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
 
 struct Plan {
   bool ok;
-  int CC, NCH, nst, resident, ctas_per_sm, lanech;
+  int CC, NCH, nst, resident, ctas_per_sm, lanech, gy_bufs;
   size_t smem;
 };
 
@@ -999,8 +1029,8 @@ inline int env_int(const char* name, int dflt) {
 }
 
 template <typename T, class C, int MODE>
-Plan plan_for(const KParams& P) {
-  Plan pl{false, 0, 0, 0, 0, 0, 0, 0};
+Plan plan_for(const KParams& P, int num_sms = 148) {
+  Plan pl{false, 0, 0, 0, 0, 0, 0, 2, 0};
   constexpr int esz = (int)sizeof(T);
   constexpr bool bwd = (MODE == MODE_BWD || MODE == MODE_POOL_BWD);
   static const int target_bytes = env_int("NFPB200_CHUNK_BYTES", 16 * 1024);
@@ -1028,12 +1058,24 @@ Plan plan_for(const KParams& P) {
   pl.CC = best;
   pl.NCH = P.C / best;
   const int max_ctas = want_ctas < 1 ? 1 : (want_ctas > C::MINB ? C::MINB : want_ctas);
+  static const int want_whole = env_int("NFPB200_RESIDENT_IMAGE", 1);
   for (int ctas = max_ctas; ctas >= 1 && !pl.ok; --ctas) {
-    const int budget = kSmemPerSM / ctas - 2048;  // the runtime reserves 1 KB per CTA; 1 KB slack
+    // one image per CTA (the whole batch fits the resident CTAs): a single upstream-gradient buffer suffices
+    const int gy_bufs = (bwd && P.B <= num_sms * ctas) ? 1 : 2;
+    const int budget = (kSmemPerSM + 1024) / ctas - 1024 - 256;  // 228 KB per SM, 1 KB reserved per CTA; 256 B slack
     static const int max_stages = env_int("NFPB200_MAX_STAGES", 5);  // measured: 4-5 stages beat 6-8 at B = 256
-    for (int nst = max_stages < kMaxStages ? max_stages : kMaxStages; nst >= 2; --nst) {  // as many stages as fit
-      Smem<T, C, MODE, kNW> L(pl.CC, nst, P.C, P.Kin);
+    int first = max_stages < kMaxStages ? max_stages : kMaxStages;
+    // backward with the lane-per-channel pass B: if the WHOLE image fits (512x7x7 fp32: 8 slots, 98 KB), keep it -- a
+    // warp owns a whole chunk in pass B, so with fewer slots than chunks the last warps wait for a slot to drain and
+    // for its refill (an L2 round trip) before they can start
+    if (pl.lanech && want_whole && !force_stream && pl.NCH <= kMaxStages && pl.NCH > first) {
+      Smem<T, C, MODE, kNW> L(pl.CC, pl.NCH, P.C, P.Kin, pl.lanech, gy_bufs);
+      if (L.total <= budget) first = pl.NCH;
+    }
+    for (int nst = first; nst >= 2; --nst) {  // as many stages as fit
+      Smem<T, C, MODE, kNW> L(pl.CC, nst, P.C, P.Kin, pl.lanech, gy_bufs);
       if (L.total > budget) continue;
+      pl.gy_bufs = gy_bufs;
       pl.nst = nst;
       pl.smem = (size_t)L.total;
       pl.ctas_per_sm = ctas;
@@ -1048,26 +1090,15 @@ Plan plan_for(const KParams& P) {
 
 template <typename T, class C, int MODE>
 int launch_mode(const KParams& P, StreamArgs a, cudaStream_t stream) {
-  const Plan pl = plan_for<T, C, MODE>(P);
-  if (!pl.ok) return NFPB200_EUNSUPPORTED;
-  a.CC = pl.CC;
-  a.NCH = pl.NCH;
-  a.nst = pl.nst;
-  a.resident = pl.resident;
-  a.lanech = pl.lanech;
-  static const int y_delay = env_int("NFPB200_Y_DELAY_NS", 0);
-  static const int y_stages = env_int("NFPB200_Y_STAGES", 0);
-  a.y_delay_ns = y_delay;
-  a.y_stages = y_stages;
-  auto kern = stream_kernel<T, C, MODE, kNW>;
-  // per-device one-time setup (function attributes are per device; a process may drive several GPUs).
-  // Idempotent, so a race between two host threads doing it at once is harmless.
   constexpr int kMaxDev = 64;
   static int sm_count[kMaxDev] = {0};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
   if (dev < 0 || dev >= kMaxDev) return NFPB200_EDEVICE;
+  auto kern = stream_kernel<T, C, MODE, kNW>;
+  // per-device one-time setup (function attributes are per device; a process may drive several GPUs).
+  // Idempotent, so a race between two host threads doing it at once is harmless.
   if (sm_count[dev] == 0) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerSM);
     if (e != cudaSuccess) return (int)e;
@@ -1077,6 +1108,18 @@ int launch_mode(const KParams& P, StreamArgs a, cudaStream_t stream) {
     sm_count[dev] = n;
   }
   const int num_sms = sm_count[dev];
+  const Plan pl = plan_for<T, C, MODE>(P, num_sms);
+  if (!pl.ok) return NFPB200_EUNSUPPORTED;
+  a.gy_bufs = pl.gy_bufs;
+  a.CC = pl.CC;
+  a.NCH = pl.NCH;
+  a.nst = pl.nst;
+  a.resident = pl.resident;
+  a.lanech = pl.lanech;
+  static const int y_delay = env_int("NFPB200_Y_DELAY_NS", 0);
+  static const int y_stages = env_int("NFPB200_Y_STAGES", 0);
+  a.y_delay_ns = y_delay;
+  a.y_stages = y_stages;
   a.nsm = num_sms;
   const Tables<C>* gt = tables_for<C>(a.pad_mode);
   if (!gt) return NFPB200_EINVAL;
