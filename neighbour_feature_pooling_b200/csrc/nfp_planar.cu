@@ -318,11 +318,123 @@ __device__ __forceinline__ void band_dots(const unsigned char* pl, int pitch, in
   }
 }
 
+// forward values of one band pixel from its window dots: yv[n], n = tap number
+template <int R, bool INTERIOR>
+__device__ __forceinline__ void band_forward_pixel(const float (&acc)[(2 * R + 1) * (2 * R + 1)], const float* inv, int ps,
+                                                   int p, int pr, int pc, const PlanarParams& q,
+                                                   float (&yv)[(2 * R + 1) * (2 * R + 1) - 1]) {
+  constexpr int k = 2 * R + 1, KK = k * k, CTR = R * k + R;
+  const float ip = inv[ps];
+#pragma unroll
+  for (int tp = 0; tp < KK; ++tp) {
+    if (tp == CTR) continue;
+    const int dy = tp / k - R, dx = tp % k - R;
+    float v_ = 0.f;
+    if constexpr (INTERIOR) {  // at least R away from every border: every tap lands on its own window entry
+      v_ = acc[tp] * (ip * inv[ps + dy * q.W + dx]);
+    } else {
+      int o;
+      const int v = tap_landing<R>(pr, pc, dy, dx, q, o);
+      if (v >= 0) {
+        float d = 0.f;   // acc[o] with a run-time o: select (the array must stay in registers)
+#pragma unroll
+        for (int oo = 0; oo < KK; ++oo) d = (oo == o) ? acc[oo] : d;
+        v_ = d * (ip * inv[ps + (v - p)]);
+      }
+    }
+    if (!q.similarity) v_ = 1.f - v_;
+    yv[tp < CTR ? tp : tp - 1] = v_;
+  }
+}
+
+// the k x k stencil coefficients of one band pixel (closed form of ATen's cosine_similarity backward, gather form):
+// w[o] multiplies x[p + off(o)]; outside the map: 0
+template <typename T, int R, bool INTERIOR>
+__device__ __forceinline__ void band_coefficients(const float (&acc)[(2 * R + 1) * (2 * R + 1)], const float* inv, int ps, int p,
+                                                  int pr, int pc, const PlanarParams& q, const T* __restrict__ gyb, float sgn,
+                                                  float (&w)[(2 * R + 1) * (2 * R + 1)]) {
+  constexpr int k = 2 * R + 1, KK = k * k, K = KK - 1, CTR = R * k + R;
+  const float t0 = acc[CTR], ip = inv[ps];
+  const float nrm = sqrtf(t0);
+  const float rnp = nrm > 0.f ? ip / nrm : 0.f;  // 1 / (N_p |x_p|): the norm term of ATen's backward, 0 at x = 0
+  float s_dot = 0.f, sw = 0.f;
+  if constexpr (INTERIOR) {  // at least 2R away from every border: neither p nor any window neighbour has a folded tap
+#pragma unroll
+    for (int o = 0; o < KK; ++o) {
+      if (o == CTR) continue;
+      const int dv = (o / k - R) * q.W + (o % k - R);
+      const int n = o < CTR ? o : o - 1;  // the direct tap of p towards v, and v's direct tap back
+      const float s = to_f32(gyb[(size_t)n * q.P + p]) + to_f32(gyb[(size_t)(K - 1 - n) * q.P + p + dv]);
+      w[o] = sgn * s * ip * inv[ps + dv];
+      s_dot = fmaf(w[o], acc[o], s_dot);
+    }
+  } else {
+    int FY[k][k], FX[k][k];
+#pragma unroll
+    for (int d = 0; d < k; ++d) {
+      fold_map<R>(pr + d - R, q.H, q.mode, FY[d]);
+      fold_map<R>(pc + d - R, q.W, q.mode, FX[d]);
+    }
+#pragma unroll
+    for (int o = 0; o < KK; ++o) {
+      if (o == CTR) continue;
+      const int oy = o / k, ox = o % k;
+      const int v = window_pixel(pr, pc, oy - R, ox - R, q);
+      w[o] = 0.f;
+      if (v >= 0) {
+        const float s = folded_taps<T, R>(gyb + p, FY[R], FX[R], oy, ox, q.P) +
+                        folded_taps<T, R>(gyb + v, FY[oy], FX[ox], k - 1 - oy, k - 1 - ox, q.P);
+        w[o] = sgn * s * ip * inv[ps + (v - p)];
+        s_dot = fmaf(w[o], acc[o], s_dot);
+      }
+    }
+    // taps of p that land on p itself (replicate padding): y = <p,p>/(N N), gradient 2 G (1/N^2 - y/(N |p|)) x_p
+    sw = 2.f * sgn * folded_taps<T, R>(gyb + p, FY[R], FX[R], R, R, q.P) * ip * ip;
+  }
+  w[CTR] = sw - rnp * (s_dot + sw * t0);
+}
+
+// The pixels of a band in two passes: first the INTERIOR ones (at least M pixels away from every border of the map:
+// straight-line code, window offsets identical for all threads, i.e. uniform-register address operands), then the few
+// border pixels of the band as a compact list (M columns on either side of every row, whole rows at the top / bottom of
+// the map) -- so that a warp which merely CONTAINS a border pixel does not drag all its lanes through the fold logic
+// (ncu on the one-pass form: 1 080 instructions per 32 pixels, most of them border code run by 57 % of the warps).
+struct BandSplit {
+  int r0, r1, ir0, ir1, IW, M, W, n_int, n_brd, nbr_top, nbr_rows;
+  __device__ BandSplit(int r0_, int TH, int H, int W_, int M_) {
+    r0 = r0_; r1 = min(r0_ + TH, H); M = M_; W = W_;
+    IW = max(W_ - 2 * M_, 0);
+    ir0 = min(max(r0, M_), r1);
+    ir1 = max(min(r1, H - M_), ir0);
+    if (IW == 0) ir1 = ir0;
+    n_int = (ir1 - ir0) * IW;
+    nbr_top = ir0 - r0;
+    nbr_rows = (r1 - r0) - (ir1 - ir0);
+    n_brd = nbr_rows * W_ + (ir1 - ir0) * (W_ - IW);
+  }
+  __device__ __forceinline__ void interior(int t, int& pr, int& pc) const {
+    const int lr = t / IW;
+    pr = ir0 + lr;
+    pc = M + (t - lr * IW);
+  }
+  __device__ __forceinline__ void border(int u, int& pr, int& pc) const {
+    if (u < nbr_rows * W) {  // whole rows above / below the interior rows
+      const int lr = u / W;
+      pc = u - lr * W;
+      pr = lr < nbr_top ? r0 + lr : ir1 + (lr - nbr_top);
+    } else {
+      const int e = W - IW, v = u - nbr_rows * W, lr = v / e, j = v - lr * e;
+      pr = ir0 + lr;
+      pc = j < M ? j : IW + j;
+    }
+  }
+};
+
 template <typename T, int R>
 __global__ void __launch_bounds__(kThreads) planar_fused_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, PlanarParams q,
                                                                     int TH, int A) {
   using Wn = Win<R>;
-  constexpr int k = Wn::k, KK = Wn::KK, CTR = Wn::CTR, ESZ = (int)sizeof(T);
+  constexpr int k = Wn::k, KK = Wn::KK, K = Wn::K, ESZ = (int)sizeof(T);
   extern __shared__ __align__(128) unsigned char sm[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm);
   unsigned char* xs = sm + 16;
@@ -331,41 +443,38 @@ __global__ void __launch_bounds__(kThreads) planar_fused_fwd_kernel(const T* __r
   band_fetch<T, R>(x, xs, bar, q, b, r0, TH, A, top, bot, pitch);
   float* inv = reinterpret_cast<float*>(xs + (size_t)q.C * pitch);
   band_norms<T>(xs, inv, q, r0, A, top, bot, pitch);
-  for (int t = threadIdx.x; t < TH * q.W; t += blockDim.x) {
-    const int lr = t / q.W, pc = t - lr * q.W, pr = r0 + lr;
-    if (pr >= q.H) break;
-    const int p = pr * q.W + pc, ps = (lr + A) * q.W + pc;   // pixel in the map / in the slab
+  const BandSplit bs(r0, TH, q.H, q.W, R);
+  T* yb0 = y + (size_t)b * K * q.P;
+  {
+    int off[KK];  // the same for every interior pixel
+#pragma unroll
+    for (int o = 0; o < KK; ++o) off[o] = ((o / k - R) * q.W + (o % k - R)) * ESZ;
+    for (int t = threadIdx.x; t < bs.n_int; t += blockDim.x) {
+      int pr, pc;
+      bs.interior(t, pr, pc);
+      const int p = pr * q.W + pc, ps = (pr - r0 + A) * q.W + pc;   // pixel in the map / in the slab
+      float acc[KK], yv[K];
+      band_dots<T, R>(xs + (size_t)ps * ESZ, pitch, q.C, off, acc);
+      band_forward_pixel<R, true>(acc, inv, ps, p, pr, pc, q, yv);
+#pragma unroll
+      for (int n = 0; n < K; ++n) yb0[(size_t)n * q.P + p] = from_f32<T>(yv[n]);
+    }
+  }
+  for (int u = threadIdx.x; u < bs.n_brd; u += blockDim.x) {
+    int pr, pc;
+    bs.border(u, pr, pc);
+    const int p = pr * q.W + pc, ps = (pr - r0 + A) * q.W + pc;
     int off[KK];
-    float acc[KK];
+    float acc[KK], yv[K];
 #pragma unroll
     for (int o = 0; o < KK; ++o) {
       const int dy = o / k - R, dx = o % k - R;
       off[o] = window_pixel(pr, pc, dy, dx, q) >= 0 ? (dy * q.W + dx) * ESZ : 0;
     }
     band_dots<T, R>(xs + (size_t)ps * ESZ, pitch, q.C, off, acc);
-    const float ip = inv[ps];
-    T* yb = y + (size_t)b * Wn::K * q.P + p;
-    const bool interior = pr >= R && pr < q.H - R && pc >= R && pc < q.W - R;
+    band_forward_pixel<R, false>(acc, inv, ps, p, pr, pc, q, yv);
 #pragma unroll
-    for (int tp = 0; tp < KK; ++tp) {
-      if (tp == CTR) continue;
-      const int dy = tp / k - R, dx = tp % k - R;
-      float yv = 0.f;
-      if (interior) {
-        yv = acc[tp] * (ip * inv[ps + dy * q.W + dx]);
-      } else {
-        int o;
-        const int v = tap_landing<R>(pr, pc, dy, dx, q, o);
-        if (v >= 0) {
-          float d = 0.f;   // acc[o] with a run-time o: select (the array must stay in registers)
-#pragma unroll
-          for (int oo = 0; oo < KK; ++oo) d = (oo == o) ? acc[oo] : d;
-          yv = d * (ip * inv[ps + (v - p)]);
-        }
-      }
-      if (!q.similarity) yv = 1.f - yv;
-      yb[(size_t)(tp < CTR ? tp : tp - 1) * q.P] = from_f32<T>(yv);
-    }
+    for (int n = 0; n < K; ++n) yb0[(size_t)n * q.P + p] = from_f32<T>(yv[n]);
   }
 }
 
@@ -373,7 +482,7 @@ template <typename T, int R>
 __global__ void __launch_bounds__(kThreads) planar_fused_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy,
                                                                     T* __restrict__ gx, PlanarParams q, int TH, int A) {
   using Wn = Win<R>;
-  constexpr int k = Wn::k, KK = Wn::KK, K = Wn::K, CTR = Wn::CTR, ESZ = (int)sizeof(T);
+  constexpr int k = Wn::k, KK = Wn::KK, K = Wn::K, ESZ = (int)sizeof(T);
   extern __shared__ __align__(128) unsigned char sm[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm);
   unsigned char* xs = sm + 16;
@@ -384,10 +493,34 @@ __global__ void __launch_bounds__(kThreads) planar_fused_bwd_kernel(const T* __r
   band_norms<T>(xs, inv, q, r0, A, top, bot, pitch);
   const float sgn = q.similarity ? 1.f : -1.f;
   const T* gyb = gy + (size_t)b * K * q.P;
-  for (int t = threadIdx.x; t < TH * q.W; t += blockDim.x) {
-    const int lr = t / q.W, pc = t - lr * q.W, pr = r0 + lr;
-    if (pr >= q.H) break;
-    const int p = pr * q.W + pc, ps = (lr + A) * q.W + pc;
+  T* gxb = gx + (size_t)b * q.C * q.P;
+  const BandSplit bs(r0, TH, q.H, q.W, 2 * R);
+  {
+    int off[KK];  // the same for every interior pixel
+#pragma unroll
+    for (int o = 0; o < KK; ++o) off[o] = ((o / k - R) * q.W + (o % k - R)) * ESZ;
+    for (int t = threadIdx.x; t < bs.n_int; t += blockDim.x) {
+      int pr, pc;
+      bs.interior(t, pr, pc);
+      const int p = pr * q.W + pc, ps = (pr - r0 + A) * q.W + pc;
+      float acc[KK], w[KK];
+      const unsigned char* pl = xs + (size_t)ps * ESZ;
+      band_dots<T, R>(pl, pitch, q.C, off, acc);
+      band_coefficients<T, R, true>(acc, inv, ps, p, pr, pc, q, gyb, sgn, w);
+      T* gp = gxb + p;
+#pragma unroll(R == 1 ? 4 : 1)
+      for (int c = 0; c < q.C; ++c, pl += pitch, gp += q.P) {
+        float a = 0.f;
+#pragma unroll
+        for (int o = 0; o < KK; ++o) a = fmaf(w[o], ptx::ldx<T>(pl + off[o]), a);
+        gp[0] = from_f32<T>(a);
+      }
+    }
+  }
+  for (int u = threadIdx.x; u < bs.n_brd; u += blockDim.x) {
+    int pr, pc;
+    bs.border(u, pr, pc);
+    const int p = pr * q.W + pc, ps = (pr - r0 + A) * q.W + pc;
     int off[KK];
     float acc[KK], w[KK];
 #pragma unroll
@@ -395,49 +528,10 @@ __global__ void __launch_bounds__(kThreads) planar_fused_bwd_kernel(const T* __r
       const int dy = o / k - R, dx = o % k - R;
       off[o] = window_pixel(pr, pc, dy, dx, q) >= 0 ? (dy * q.W + dx) * ESZ : 0;
     }
-    const unsigned char* pl0 = xs + (size_t)ps * ESZ;
-    band_dots<T, R>(pl0, pitch, q.C, off, acc);
-    const float t0 = acc[CTR], ip = inv[ps];
-    const float nrm = sqrtf(t0);
-    const float rnp = nrm > 0.f ? ip / nrm : 0.f;  // 1 / (N_p |x_p|): the norm term of ATen's backward, 0 at x = 0
-    const bool interior = pr >= 2 * R && pr < q.H - 2 * R && pc >= 2 * R && pc < q.W - 2 * R;
-    float s_dot = 0.f, sw = 0.f;
-    if (interior) {
-#pragma unroll
-      for (int o = 0; o < KK; ++o) {
-        if (o == CTR) continue;
-        const int dv = (o / k - R) * q.W + (o % k - R);
-        const int n = o < CTR ? o : o - 1;  // the direct tap of p towards v, and v's direct tap back
-        const float s = to_f32(gyb[(size_t)n * q.P + p]) + to_f32(gyb[(size_t)(K - 1 - n) * q.P + p + dv]);
-        w[o] = sgn * s * ip * inv[ps + dv];
-        s_dot = fmaf(w[o], acc[o], s_dot);
-      }
-    } else {
-      int FY[k][k], FX[k][k];
-#pragma unroll
-      for (int d = 0; d < k; ++d) {
-        fold_map<R>(pr + d - R, q.H, q.mode, FY[d]);
-        fold_map<R>(pc + d - R, q.W, q.mode, FX[d]);
-      }
-#pragma unroll
-      for (int o = 0; o < KK; ++o) {
-        if (o == CTR) continue;
-        const int oy = o / k, ox = o % k;
-        const int v = window_pixel(pr, pc, oy - R, ox - R, q);
-        w[o] = 0.f;
-        if (v >= 0) {
-          const float s = folded_taps<T, R>(gyb + p, FY[R], FX[R], oy, ox, q.P) +
-                          folded_taps<T, R>(gyb + v, FY[oy], FX[ox], k - 1 - oy, k - 1 - ox, q.P);
-          w[o] = sgn * s * ip * inv[ps + (v - p)];
-          s_dot = fmaf(w[o], acc[o], s_dot);
-        }
-      }
-      // taps of p that land on p itself (replicate padding): y = <p,p>/(N N), gradient 2 G (1/N^2 - y/(N |p|)) x_p
-      sw = 2.f * sgn * folded_taps<T, R>(gyb + p, FY[R], FX[R], R, R, q.P) * ip * ip;
-    }
-    w[CTR] = sw - rnp * (s_dot + sw * t0);
-    const unsigned char* pl = pl0;
-    T* gp = gx + (size_t)b * q.C * q.P + p;
+    const unsigned char* pl = xs + (size_t)ps * ESZ;
+    band_dots<T, R>(pl, pitch, q.C, off, acc);
+    band_coefficients<T, R, false>(acc, inv, ps, p, pr, pc, q, gyb, sgn, w);
+    T* gp = gxb + p;
 #pragma unroll(R == 1 ? 4 : 1)
     for (int c = 0; c < q.C; ++c, pl += pitch, gp += q.P) {
       float a = 0.f;
@@ -518,9 +612,9 @@ int forward_r(const KParams& P, const T* x, T* y, const LaunchCtx& ctx) {
   const PlanarParams q = make(P);
   const BandPlan fp = fused_plan(P, (int)sizeof(T));
   if (fp.ok) {  // one launch, no workspace
+    const dim3 bgrid((unsigned)((q.H + fp.TH - 1) / fp.TH), (unsigned)q.B);
     auto kern = planar_fused_fwd_kernel<T, R>;
     if (cudaError_t e = allow_smem(kern, fp.smem)) return (int)e;
-    const dim3 bgrid((unsigned)((q.H + fp.TH - 1) / fp.TH), (unsigned)q.B);
     kern<<<bgrid, fp.threads, fp.smem, ctx.stream>>>(x, y, q, fp.TH, fp.A);
     return (int)cudaGetLastError();
   }
@@ -535,9 +629,9 @@ int backward_r(const KParams& P, const T* x, const T* gy, T* gx, const LaunchCtx
   const PlanarParams q = make(P);
   const BandPlan fp = fused_plan(P, (int)sizeof(T));
   if (fp.ok) {  // one launch, no workspace
+    const dim3 bgrid((unsigned)((q.H + fp.TH - 1) / fp.TH), (unsigned)q.B);
     auto kern = planar_fused_bwd_kernel<T, R>;
     if (cudaError_t e = allow_smem(kern, fp.smem)) return (int)e;
-    const dim3 bgrid((unsigned)((q.H + fp.TH - 1) / fp.TH), (unsigned)q.B);
     kern<<<bgrid, fp.threads, fp.smem, ctx.stream>>>(x, gy, gx, q, fp.TH, fp.A);
     return (int)cudaGetLastError();
   }
