@@ -705,6 +705,43 @@ def main():
                           "us_per_step_launch_per_radius": (sep[0]["us_per_step"] + sep[1]["us_per_step"]) if all(sep) else None})
             del s
             torch.cuda.empty_cache()
+    # ---- the five maps of MobileNetV3_MultiStageNFP (models/texture_pooling.py:211-268) fwd + bwd, B = 64: one CUDA-graph
+    # replay of all ten calls (planar row-band kernels for the three large maps, ring kernels for the two small ones)
+    multi_stage = None
+    if not args.no_sweep and rank == 0:
+        maps = [(16, 112, 112), (24, 56, 56), (40, 28, 28), (112, 14, 14), (960, 7, 7)]
+        lbs = [LayerBench(dev, 64, c, h, w, 1, "fp32") for c, h, w in maps]
+
+        def all_maps(i):
+            for s_ in lbs:
+                s_.fwd(i % s_.nbuf)
+            for s_ in reversed(lbs):
+                s_.bwd_conservative(i % s_.nbuf)
+        for i in range(3):
+            all_maps(i)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(4):
+                all_maps(i)
+        g.replay()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.tag = "sweep"
+        e0.record()
+        for _ in range(10):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        sampler.tag = None
+        algo = sum(sum(algorithmic_bytes(64, c, h, w, 1, 4)) for c, h, w in maps)
+        t_set = e0.elapsed_time(e1) * 1e-3 / 40
+        multi_stage = {"workload": "nfp_cosine_fwd_bwd B=64 fp32, the five maps of MobileNetV3_MultiStageNFP "
+                                   "(16x112x112, 24x56x56, 40x28x28, 112x14x14, 960x7x7)",
+                       "us_per_set": t_set * 1e6, "launches_per_set": sum(s_.launches for s_ in lbs),
+                       "paths": [s_.path_bwd for s_ in lbs], "set_frac": algo / t_set / 1e9 / hbm_peak}
+        del lbs, g
+        torch.cuda.empty_cache()
     # ---- metric part (ii): ResNet18 + NFP training images/s (DDP over NCCL when N > 1) ---------------------------
     train = None
     if not args.no_train:
@@ -793,6 +830,8 @@ def main():
             line["sweep"] = sweep
         if multi:
             line["multi_radius"] = multi
+        if multi_stage:
+            line["multi_stage"] = multi_stage
         if train is not None:
             line["train"] = train
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
