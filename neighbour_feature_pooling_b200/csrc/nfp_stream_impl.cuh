@@ -51,6 +51,20 @@
 
 #include "nfp_tables.cuh"
 
+// timing experiments (variant builds only -- `python -m neighbour_feature_pooling_b200.build --variant x -DNFP_DBG_...=1`,
+// selected with NFPB200_LIB; results are wrong): compile out the arithmetic of pass A / everything after pass A in the
+// forward / the forward's value loop, to see what the launch structure alone costs
+// (profiles/r02_ubench_cold_read_floor.txt)
+#ifndef NFP_DBG_SKIP_PASSA
+#define NFP_DBG_SKIP_PASSA 0
+#endif
+#ifndef NFP_DBG_SKIP_TAIL
+#define NFP_DBG_SKIP_TAIL 0
+#endif
+#ifndef NFP_DBG_SKIP_EPI
+#define NFP_DBG_SKIP_EPI 0
+#endif
+
 namespace nfp {
 namespace stream {
 
@@ -454,7 +468,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
           }
           const unsigned char* pa = sl + warp * PSTRIDE + toff;
           for (int it = warp; it < npairs; it += NW, pa += NW * PSTRIDE) {
-            if (lane_on) {
+            if (lane_on && !NFP_DBG_SKIP_PASSA) {
               uint64_t xr[R + 1][XW];
 #pragma unroll
               for (int dy = 0; dy <= R; ++dy)
@@ -514,7 +528,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
           }
           const unsigned char* pa = sl + warp * PSTRIDE + toff;
           for (int it = warp; it < npairs; it += NW, pa += NW * PSTRIDE) {
-            if (lane_on) {
+            if (lane_on && !NFP_DBG_SKIP_PASSA) {
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const unsigned char* ph_ = pa + h * GSTRIDE;
@@ -549,6 +563,10 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
           phbits ^= 1u << slot;
           if (++slot == nactA) slot = 0;
         }
+      }
+      if constexpr (NFP_DBG_SKIP_TAIL && !BWD) {
+        consumer_sync<NT>();
+        continue;
       }
       // sum over the channel slots of the warp (fixed shuffle tree: deterministic), then publish the warp's table
       if constexpr (CPW > 1) {
@@ -615,7 +633,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
       const int16_t* fv = reinterpret_cast<const int16_t*>(smem_raw + L.t_fv);
       const int16_t* fd = reinterpret_cast<const int16_t*>(smem_raw + L.t_fd);
       float* ytab = reinterpret_cast<float*>(smem_raw + L.ytab);
-      for (int idx = tid; idx < K * P; idx += NT) {
+      for (int idx = tid; idx < (NFP_DBG_SKIP_EPI ? 0 : K * P); idx += NT) {
         const int p = idx % P;
         const int v = fv[idx];
         float yv = 0.f;
