@@ -104,8 +104,12 @@ FUSED_SHAPES = [(5, 64, 7, 7, 1), (3, 512, 7, 7, 1), (2, 960, 7, 7, 1), (3, 256,
 
 PLANAR_SHAPES = [(2, 16, 112, 112, 1), (2, 24, 56, 56, 1), (3, 40, 28, 28, 1), (2, 7, 9, 13, 1), (2, 5, 3, 3, 1),
                  (2, 12, 28, 28, 2), (1, 6, 11, 13, 3), (3, 33, 7, 7, 1), (2, 10, 5, 9, 2),
-                 (2, 5, 8, 6, 1), (70, 3, 12, 8, 1), (1, 4, 16, 20, 2)]   # row granule 2 / many images
-PLANAR_BAND = {(16, 112, 112), (24, 56, 56), (40, 28, 28), (12, 28, 28), (5, 8, 6), (3, 12, 8), (4, 16, 20)}
+                 (2, 5, 8, 6, 1), (70, 3, 12, 8, 1), (1, 4, 16, 20, 2),   # row granule 2 / many images
+                 # the band kernels' interior / border split at its corners: no interior rows, no interior columns,
+                 # a one-row last band, a 5x5 window on a map narrower than its backward margin
+                 (2, 8, 4, 12, 1), (2, 4, 20, 4, 1), (3, 6, 33, 16, 1), (1, 4, 5, 8, 2)]
+PLANAR_BAND = {(16, 112, 112), (24, 56, 56), (40, 28, 28), (12, 28, 28), (5, 8, 6), (3, 12, 8), (4, 16, 20),
+               (8, 4, 12), (4, 20, 4), (6, 33, 16), (4, 5, 8)}
 
 
 @pytest.mark.parametrize("shape", PLANAR_SHAPES, ids=lambda s: "x".join(map(str, s[:4])) + f"_r{s[4]}")
