@@ -59,9 +59,44 @@ def _case(NFPPooling, measure, geom, similarity, p, seed, relu):
     return out
 
 
+def multi_radius(NFPPooling):
+    """The operator inside the reference's MultiRadiusNFPHead (models/nfp_heads.py:86-93,111-112), executed with the
+    reference's own NFPPooling (the head's EnhancedNFPPooling is the symbol the reference does not ship): R_list = (1, 2),
+    padding = R, then torch.cat along the channels; fp64 on fp32 values, input gradient for a seeded upstream gradient."""
+    arrays, index = {}, []
+    for i, (B, C, H, W, mode, similarity) in enumerate([(3, 64, 7, 7, "reflect", True), (2, 16, 14, 14, "reflect", True),
+                                                       (2, 64, 7, 7, "replicate", False), (2, 8, 7, 7, "zeros", True)]):
+        gen = torch.Generator().manual_seed(4000 + i)
+        x32 = torch.randn(B, C, H, W, generator=gen)
+        if i % 2 == 0:
+            x32 = x32.relu()
+        blocks = [NFPPooling(C, R=R, measure="cosine", padding=R, padding_mode=mode, similarity=similarity).double()
+                  for R in (1, 2)]
+        xr = x32.double().requires_grad_(True)
+        nfp_maps = [blk(xr) for blk in blocks]
+        nfp_cat = torch.cat(nfp_maps, dim=1)
+        g32 = torch.randn(nfp_cat.shape, generator=gen)
+        (gx,) = torch.autograd.grad(nfp_cat, xr, g32.double())
+        key = f"m{i}"
+        arrays.update({f"{key}_x": x32.numpy(), f"{key}_g": g32.numpy(), f"{key}_y": nfp_cat.detach().numpy(),
+                       f"{key}_gx": gx.numpy()})
+        index.append(dict(key=key, B=B, C=C, H=H, W=W, padding_mode=mode, similarity=similarity))
+    np.savez_compressed(os.path.join(OUT_DIR, "nfp_multi_radius.npz"), **arrays)
+    with open(os.path.join(OUT_DIR, "nfp_multi_radius.json"), "w") as f:
+        json.dump(dict(generator="oracle/make_golden.py --multi-radius", torch=torch.__version__,
+                       reference="models/pooling/nfp.py NFPPooling x 2 (R = 1, 2; padding = R) + torch.cat, as "
+                                 "models/nfp_heads.py:86-93,111-112 composes them (unmodified, CPU, fp64)",
+                       cases=index), f, indent=1)
+
+
 def main():
     NFPPooling, nfp_pooling = load_reference()
     os.makedirs(OUT_DIR, exist_ok=True)
+    import sys
+    if "--multi-radius" in sys.argv:   # only this fixture (the others stay byte-identical)
+        multi_radius(NFPPooling)
+        print("multi-radius fixture written to", OUT_DIR)
+        return
     arrays, index = {}, []
     cid = 0
     for measure in MEASURE_SPELLINGS:
@@ -124,6 +159,7 @@ def main():
     np.savez_compressed(os.path.join(OUT_DIR, "nfp_state_dict.npz"),
                         **{"cosine_" + k: v.numpy() for k, v in sd.items()},
                         **{"norm_" + k: v.numpy() for k, v in sdn.items()})
+    multi_radius(NFPPooling)
     print("golden fixtures written to", OUT_DIR)
     for fn in sorted(os.listdir(OUT_DIR)):
         print(f"  {fn}: {os.path.getsize(os.path.join(OUT_DIR, fn))} bytes")

@@ -22,6 +22,13 @@ def load_wrapper_cases():
     return index, arrays
 
 
+def load_multi_radius_cases():
+    with open(os.path.join(GOLDEN, "nfp_multi_radius.json")) as f:
+        index = json.load(f)["cases"]
+    arrays = np.load(os.path.join(GOLDEN, "nfp_multi_radius.npz"))
+    return index, arrays
+
+
 def case_kwargs(c):
     return dict(R=c["R"], measure=c["measure"], p=c["p"], stride=c["stride"], padding=c["padding"],
                 dilation=c["dilation"], padding_mode=c["padding_mode"], similarity=c["similarity"])

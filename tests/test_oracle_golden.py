@@ -7,7 +7,7 @@ import torch
 from oracle import nfp_oracle as O
 from oracle.ref_loader import reference_available
 
-from _util import case_id, case_kwargs, load_measure_cases, load_wrapper_cases, rel_err
+from _util import case_id, case_kwargs, load_measure_cases, load_multi_radius_cases, load_wrapper_cases, rel_err
 
 INDEX, ARR = load_measure_cases()
 
@@ -33,6 +33,28 @@ def test_closed_form_cosine_matches_golden(c):
     # the reference's own fp32 rounding noise is far below the 1e-5 parity bar of the CUDA path
     assert rel_err(ARR[c["key"] + "_y_f32"], ARR[c["key"] + "_y_f64"]) < 2e-6
     assert rel_err(ARR[c["key"] + "_gx_f32"], ARR[c["key"] + "_gx_f64"]) < 2e-6
+
+
+def test_multi_radius_golden_and_nesting():
+    """The reference's multi-radius composition (two NFPPooling layers, R = 1, 2, padding = R, torch.cat -- as
+    models/nfp_heads.py:86-93,111-112 builds it): the oracle reproduces it layer by layer, and the radius-1 map is exactly the
+    inner taps of the radius-2 map (what lets the CUDA path produce both from one pass, include/nfp_b200.h inner_R)."""
+    index, arr = load_multi_radius_cases()
+    inner = [6, 7, 8, 11, 12, 15, 16, 17]   # taps of the 5x5 window (centre removed) with |dy|, |dx| <= 1, row-major
+    for c in index:
+        x = torch.from_numpy(arr[c["key"] + "_x"]).double()
+        g = torch.from_numpy(arr[c["key"] + "_g"]).double()
+        ys, gxs = [], []
+        for R, sl in ((1, slice(0, 8)), (2, slice(8, 32))):
+            y, gx = O.nfp_forward_backward(x, g[:, sl].contiguous(), R=R, measure="cosine", padding=R,
+                                           padding_mode=c["padding_mode"], similarity=c["similarity"])
+            ys.append(torch.as_tensor(np.asarray(y)))
+            gxs.append(torch.as_tensor(np.asarray(gx)))
+        assert rel_err(torch.cat(ys, 1), arr[c["key"] + "_y"]) < 1e-12
+        assert rel_err(gxs[0] + gxs[1], arr[c["key"] + "_gx"]) < 1e-10
+        y_ref = torch.from_numpy(arr[c["key"] + "_y"])
+        # radius-1 map = inner taps of the radius-2 map (the reference's two convs sum in different orders: 1e-16 apart)
+        assert rel_err(y_ref[:, :8], y_ref[:, 8:][:, inner]) < 1e-13
 
 
 def test_wrapper_golden():

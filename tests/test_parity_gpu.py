@@ -17,7 +17,7 @@ import neighbour_feature_pooling_b200 as nfpb
 from neighbour_feature_pooling_b200 import NFPPooling, nfp_pooling, functional as NF
 from oracle import nfp_oracle as O
 
-from _util import case_id, case_kwargs, load_measure_cases, load_wrapper_cases, rel_err
+from _util import case_id, case_kwargs, load_measure_cases, load_multi_radius_cases, load_wrapper_cases, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -858,6 +858,33 @@ def test_multi_radius_one_launch_vs_oracle(shape, mode, similarity, dtype, cuda_
     y3 = blocks(x3)
     y3.backward(g.to(cuda_device, dtype))
     assert torch.equal(y3, y) and torch.equal(x3.grad, xd.grad)
+
+
+def test_multi_radius_golden(cuda_device):
+    """The one-launch multi-radius path against vectors generated by executing the reference itself (two NFPPooling
+    layers + torch.cat, tests/golden/nfp_multi_radius.*), fp32 <= 1e-5; the channels-last bf16 path <= 2e-2."""
+    index, arr = load_multi_radius_cases()
+    for c in index:
+        x = torch.from_numpy(arr[c["key"] + "_x"])
+        g = torch.from_numpy(arr[c["key"] + "_g"])
+        mr = nfpb.MultiRadiusNFP(c["C"], padding_mode=c["padding_mode"], similarity=c["similarity"]).to(cuda_device)
+        NF.PATH_TRACE = set()
+        try:
+            xd = x.to(cuda_device).requires_grad_(True)
+            y = mr(xd)
+            y.backward(g.to(cuda_device))
+            trace = set(NF.PATH_TRACE)
+        finally:
+            NF.PATH_TRACE = None
+        assert any("radii 1+2 in one launch" in t for t in trace), (c, trace)
+        assert rel_err(y.detach().cpu(), arr[c["key"] + "_y"]) < FP32_TOL, c
+        assert rel_err(xd.grad.cpu(), arr[c["key"] + "_gx"]) < FP32_TOL, c
+        if c["C"] % 64 == 0:   # channels-last bf16: tensor-core token kernels, against the fp64 reference on the fp32 values
+            xb = x.to(cuda_device, torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+            yb = mr(xb)
+            yb.backward(g.to(cuda_device, torch.bfloat16))
+            assert rel_err(yb.detach().float().cpu(), arr[c["key"] + "_y"]) < BF16_TOL, c
+            assert rel_err(xb.grad.float().cpu(), arr[c["key"] + "_gx"]) < 3e-2, c   # + the rounding of x and g to bf16
 
 
 @pytest.mark.parametrize("shape", [(5, 64, 7, 7), (3, 512, 7, 7), (2, 64, 14, 14), (200, 64, 7, 7)],
