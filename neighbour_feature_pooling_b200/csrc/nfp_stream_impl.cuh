@@ -55,6 +55,10 @@
 // selected with NFPB200_LIB; results are wrong): compile out the arithmetic of pass A / everything after pass A in the
 // forward / the forward's value loop, to see what the launch structure alone costs
 // (profiles/r02_ubench_cold_read_floor.txt)
+// forward: per-lane partial tables instead of the shuffle tree over the channel slots (A/B switch)
+#ifndef NFP_FWD_DIRECT_PUBLISH
+#define NFP_FWD_DIRECT_PUBLISH 1
+#endif
 #ifndef NFP_DBG_SKIP_PASSA
 #define NFP_DBG_SKIP_PASSA 0
 #endif
@@ -98,6 +102,11 @@ struct Smem {
   // backward pass A publishes its per-warp tables in two rounds (upper half of the warps, then the lower half adds its
   // own on top): half the table space, one more barrier -- what lets a 512x7x7 fp32 image stay resident (below)
   static constexpr int NWT = BWD ? NW / 2 : NW;
+  // forward: every lane publishes its own partial table (no shuffle tree over the channel slots; the table sum then
+  // runs over NW * CPW tables) -- the forward has the shared memory for it, and its tail is latency-bound
+  // (7x7 maps: 32 tables, -0.25 us; with 64 / 128 tables on 4x4 / 2x2 maps the longer sum costs more than the tree)
+  static constexpr bool DIRECT = !BWD && (C::CPW > 1) && (C::CPW <= 4) && (NFP_FWD_DIRECT_PUBLISH != 0);
+  static constexpr int NTAB = DIRECT ? NW * C::CPW : NWT;
   // lanech: the lane-per-channel pass B is in use -> no per-warp store staging, no pads between the ring slots (it
   // reads no halo; pass A's halo reads feed accumulators nobody uses, so they may land in the next slot);
   // gy_bufs: upstream-gradient buffers (1 when every CTA handles a single image)
@@ -125,7 +134,7 @@ struct Smem {
       t_q = t_fsrc = t_fdst = t_fptr = 0;
     }
     uni = o;
-    wtab = take(NWT * C::PNV * 4);  // partial tables of the warps (their channel slots are summed by shuffles first)
+    wtab = take(NTAB * C::PNV * 4);  // partial tables of the warps (their channel slots are summed by shuffles first)
     const int u1 = o;
     o = uni;
     stg_warp = 2 * align_up(2 * C::CPW * C::P * ESZ, 16);
@@ -569,7 +578,17 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
         continue;
       }
       // sum over the channel slots of the warp (fixed shuffle tree: deterministic), then publish the warp's table
-      if constexpr (CPW > 1) {
+      constexpr bool DIRECT = Smem<T, C, MODE, NW>::DIRECT;
+      if constexpr (DIRECT) {
+        if (lane_on) {
+          float* wt = wtab + (warp * CPW + chslot) * PNV + pos * (TW * NV);
+#pragma unroll
+          for (int j = 0; j < TW; ++j)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) wt[j * NV + v] = accs[j][v];
+        }
+      }
+      if constexpr (CPW > 1 && !DIRECT) {
 #pragma unroll
         for (int d = LANES / 2; d >= NS; d >>= 1)
 #pragma unroll
@@ -578,7 +597,8 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
             for (int v = 0; v < NV; ++v) accs[j][v] += __shfl_down_sync(0xffffffffu, accs[j][v], d);
       }
       constexpr int NWT = Smem<T, C, MODE, NW>::NWT;
-      if constexpr (NWT == NW) {
+      if constexpr (DIRECT) {
+      } else if constexpr (NWT == NW) {
         if (lane < NS) {
           float* wt = wtab + warp * PNV + pos * (TW * NV);
 #pragma unroll
@@ -617,7 +637,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
     for (int i = tid; i < PNV; i += NT) {
       float s = 0.f;
 #pragma unroll 8
-      for (int t = 0; t < Smem<T, C, MODE, NW>::NWT; ++t) s += wtab[t * PNV + i];  // fixed order: deterministic
+      for (int t = 0; t < Smem<T, C, MODE, NW>::NTAB; ++t) s += wtab[t * PNV + i];  // fixed order: deterministic
       tfull[i] = s;
       if (i % NV == 0) {  // |x_p|^2: the clamped inverse norm (and, backward, the 1/(N |x|) of the norm term)
         const int p = i / NV;
