@@ -36,6 +36,7 @@ struct StreamArgs {
   int nsm;       // SMs of the device: CTAs with blockIdx >= nsm are the second CTA of their SM
   int y_delay_ns, y_stages;  // experiment knobs for those second CTAs (NFPB200_Y_DELAY_NS / NFPB200_Y_STAGES)
   int y_f32;     // forward: y is fp32 regardless of T
+  int bdirect;   // backward: per-lane partial tables (no shuffle tree over the channel slots), see Smem
   int gy_bufs;   // backward: upstream-gradient buffers in shared memory (1 when every CTA handles a single image)
   int kin, rin;  // multi-radius launch (desc.inner_R): y / gy carry kin extra channels per image (the radius-rin map) in front
   int ggx_tma;   // pooled backward: g_gap_x rows are 16-byte aligned and sized -> fetched with one bulk copy per image

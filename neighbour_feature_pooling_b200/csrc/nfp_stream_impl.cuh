@@ -110,7 +110,9 @@ struct Smem {
   // lanech: the lane-per-channel pass B is in use -> no per-warp store staging, no pads between the ring slots (it
   // reads no halo; pass A's halo reads feed accumulators nobody uses, so they may land in the next slot);
   // gy_bufs: upstream-gradient buffers (1 when every CTA handles a single image)
-  __host__ __device__ Smem(int CC, int nst, int Cfull, int kin = 0, int lanech = 0, int gy_bufs = 2) {
+  // bdirect: the BACKWARD publishes per-lane tables too (run-time choice: it costs 27 KB, i.e. the resident image)
+  static constexpr bool BDIRECT_OK = BWD && (C::CPW > 1) && (C::CPW <= 4);
+  __host__ __device__ Smem(int CC, int nst, int Cfull, int kin = 0, int lanech = 0, int gy_bufs = 2, int bdirect = 0) {
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 127) & ~127; return r; };
     // everything whose size is known at compile time comes first (so its address is a constant in the
@@ -134,7 +136,7 @@ struct Smem {
       t_q = t_fsrc = t_fdst = t_fptr = 0;
     }
     uni = o;
-    wtab = take(NTAB * C::PNV * 4);  // partial tables of the warps (their channel slots are summed by shuffles first)
+    wtab = take(((BDIRECT_OK && bdirect) ? NW * C::CPW : NTAB) * C::PNV * 4);  // partial tables of the warps / lanes
     const int u1 = o;
     o = uni;
     stg_warp = 2 * align_up(2 * C::CPW * C::P * ESZ, 16);
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int nst = a.nst, NCH = a.NCH, CC = a.CC;
-  const Smem<T, C, MODE, NW> L(CC, nst, a.C, a.kin, BWD && a.lanech, a.gy_bufs);
+  const Smem<T, C, MODE, NW> L(CC, nst, a.C, a.kin, BWD && a.lanech, a.gy_bufs, a.bdirect);
   unsigned char* ring = smem_raw + L.ring;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
   uint64_t* empty = full + kMaxStages;
@@ -579,7 +581,8 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
       }
       // sum over the channel slots of the warp (fixed shuffle tree: deterministic), then publish the warp's table
       constexpr bool DIRECT = Smem<T, C, MODE, NW>::DIRECT;
-      if constexpr (DIRECT) {
+      const bool direct = DIRECT || (Smem<T, C, MODE, NW>::BDIRECT_OK && a.bdirect);
+      if (direct) {
         if (lane_on) {
           float* wt = wtab + (warp * CPW + chslot) * PNV + pos * (TW * NV);
 #pragma unroll
@@ -588,7 +591,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
             for (int v = 0; v < NV; ++v) wt[j * NV + v] = accs[j][v];
         }
       }
-      if constexpr (CPW > 1 && !DIRECT) {
+      if (CPW > 1 && !direct) {
 #pragma unroll
         for (int d = LANES / 2; d >= NS; d >>= 1)
 #pragma unroll
@@ -597,7 +600,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
             for (int v = 0; v < NV; ++v) accs[j][v] += __shfl_down_sync(0xffffffffu, accs[j][v], d);
       }
       constexpr int NWT = Smem<T, C, MODE, NW>::NWT;
-      if constexpr (DIRECT) {
+      if (direct) {
       } else if constexpr (NWT == NW) {
         if (lane < NS) {
           float* wt = wtab + warp * PNV + pos * (TW * NV);
@@ -637,7 +640,8 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
     for (int i = tid; i < PNV; i += NT) {
       float s = 0.f;
 #pragma unroll 8
-      for (int t = 0; t < Smem<T, C, MODE, NW>::NTAB; ++t) s += wtab[t * PNV + i];  // fixed order: deterministic
+      const int ntab = (Smem<T, C, MODE, NW>::BDIRECT_OK && a.bdirect) ? NW * CPW : Smem<T, C, MODE, NW>::NTAB;
+      for (int t = 0; t < ntab; ++t) s += wtab[t * PNV + i];  // fixed order: deterministic
       tfull[i] = s;
       if (i % NV == 0) {  // |x_p|^2: the clamped inverse norm (and, backward, the 1/(N |x|) of the norm term)
         const int p = i / NV;
@@ -1057,7 +1061,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
 
 struct Plan {
   bool ok;
-  int CC, NCH, nst, resident, ctas_per_sm, lanech, gy_bufs;
+  int CC, NCH, nst, resident, ctas_per_sm, lanech, gy_bufs, bdirect;
   size_t smem;
 };
 
@@ -1068,7 +1072,7 @@ inline int env_int(const char* name, int dflt) {
 
 template <typename T, class C, int MODE>
 Plan plan_for(const KParams& P, int num_sms = 148) {
-  Plan pl{false, 0, 0, 0, 0, 0, 0, 2, 0};
+  Plan pl{false, 0, 0, 0, 0, 0, 0, 2, 0, 0};
   constexpr int esz = (int)sizeof(T);
   constexpr bool bwd = (MODE == MODE_BWD || MODE == MODE_POOL_BWD);
   static const int target_bytes = env_int("NFPB200_CHUNK_BYTES", 16 * 1024);
@@ -1103,6 +1107,22 @@ Plan plan_for(const KParams& P, int num_sms = 148) {
     const int budget = (kSmemPerSM + 1024) / ctas - 1024 - 256;  // 228 KB per SM, 1 KB reserved per CTA; 256 B slack
     static const int max_stages = env_int("NFPB200_MAX_STAGES", 5);  // measured: 4-5 stages beat 6-8 at B = 256
     int first = max_stages < kMaxStages ? max_stages : kMaxStages;
+    // one image per CTA, lane-per-channel pass B: per-lane partial tables (no shuffle tree, one publish round) with the
+    // image streamed twice, instead of the resident image with the two-round publish (NFPB200_BWD_DIRECT=0: off)
+    static const int want_bdirect = env_int("NFPB200_BWD_DIRECT", 1);
+    if (Smem<T, C, MODE, kNW>::BDIRECT_OK && want_bdirect && pl.lanech && gy_bufs == 1 && !force_stream) {
+      for (int nst = first; nst >= 3 && !pl.ok; --nst) {
+        Smem<T, C, MODE, kNW> L(pl.CC, nst, P.C, P.Kin, pl.lanech, gy_bufs, 1);
+        if (L.total > budget) continue;
+        pl.gy_bufs = gy_bufs;
+        pl.bdirect = 1;
+        pl.nst = nst;
+        pl.smem = (size_t)L.total;
+        pl.ctas_per_sm = ctas;
+        pl.ok = true;
+      }
+      if (pl.ok) break;
+    }
     // backward with the lane-per-channel pass B: if the WHOLE image fits (512x7x7 fp32: 8 slots, 98 KB), keep it -- a
     // warp owns a whole chunk in pass B, so with fewer slots than chunks the last warps wait for a slot to drain and
     // for its refill (an L2 round trip) before they can start
@@ -1149,6 +1169,7 @@ int launch_mode(const KParams& P, StreamArgs a, cudaStream_t stream) {
   const Plan pl = plan_for<T, C, MODE>(P, num_sms);
   if (!pl.ok) return NFPB200_EUNSUPPORTED;
   a.gy_bufs = pl.gy_bufs;
+  a.bdirect = pl.bdirect;
   a.CC = pl.CC;
   a.NCH = pl.NCH;
   a.nst = pl.nst;
