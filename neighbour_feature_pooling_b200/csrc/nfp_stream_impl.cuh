@@ -634,13 +634,14 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
       stencil_part();
     }
     consumer_sync<NT>();
+    NFP_STAMP(5);  // every warp's partial tables are published
     if constexpr (!BWD) {
       if (img == 0) mbar_wait(tabfull, 0);  // stencil tables (fetched by the producer at kernel start)
     }
     for (int i = tid; i < PNV; i += NT) {
+      const int ntab = (Smem<T, C, MODE, NW>::BDIRECT_OK && a.bdirect) ? NW * CPW : Smem<T, C, MODE, NW>::NTAB;
       float s = 0.f;
 #pragma unroll 8
-      const int ntab = (Smem<T, C, MODE, NW>::BDIRECT_OK && a.bdirect) ? NW * CPW : Smem<T, C, MODE, NW>::NTAB;
       for (int t = 0; t < ntab; ++t) s += wtab[t * PNV + i];  // fixed order: deterministic
       tfull[i] = s;
       if (i % NV == 0) {  // |x_p|^2: the clamped inverse norm (and, backward, the 1/(N |x|) of the norm term)
@@ -651,6 +652,7 @@ __global__ void __launch_bounds__(block_threads(MODE, NW), C::MINB) stream_kerne
       }
     }
     consumer_sync<NT>();
+    NFP_STAMP(6);  // table summed, inverse norms ready
 
     // ---- forward value -----------------------------------------------------------------------------
     if constexpr (!BWD) {

@@ -53,6 +53,13 @@ for which, fn in (("fwd", lb.fwd), ("bwd", lb.bwd)):
             col = (s[:, k] - t0) / 1e3
             line += f" {nm}: min {col.min():.1f} med {col.median():.1f} max {col.max():.1f} |"
         print(line)
+        if args.layout == "nchw" and (s[:, 5] > 0).any() and not (s[:, 7] > 0).any():   # ring kernels: stamps 5 / 6
+            d51 = (s[:, 5] - s[:, 1]) / 1e3
+            d65 = (s[:, 6] - s[:, 5]) / 1e3
+            d26 = (s[:, 2] - s[:, 6]) / 1e3
+            print(f"   per CTA: pass A (warp 0) -> all warps published: med {d51.median():.2f} max {d51.max():.2f} | -> table summed: med "
+                  f"{d65.median():.2f} max {d65.max():.2f} | -> {'values written' if which == 'fwd' else 'coefficients ready'}: med "
+                  f"{d26.median():.2f} max {d26.max():.2f} us")
         if args.layout == "nhwc":   # token kernels: stamps 0..6 per (CTA, image), durations since the row's own start
             nm = ["landed", "stencil", "gram", "coef", "Mbuilt", "done"]
             line = "   per (CTA, image) since its start |"
@@ -62,7 +69,7 @@ for which, fn in (("fwd", lb.fwd), ("bwd", lb.bwd)):
                     col = (s[ok, kk] - s[ok, 0]) / 1e3
                     line += f" {nm[kk - 1]}: {col.median():.2f} ({col.min():.2f}..{col.max():.2f}) |"
             print(line)
-        elif (s[:, 5] > 0).any():
+        elif (s[:, 7] > 0).any():
             line = f"   per-CTA (since its own start; start = {((s[:, 0] - t0) / 1e3).median():.1f} med / {((s[:, 0] - t0) / 1e3).max():.1f} max us after the first CTA) |"
             for k, nm in split_order[which]:
                 col = (s[:, k] - s[:, 0]) / 1e3
