@@ -99,7 +99,9 @@ def test_random_vs_oracle_generic(measure, geom, cuda_device):
 
 FUSED_SHAPES = [(5, 64, 7, 7, 1), (3, 512, 7, 7, 1), (2, 960, 7, 7, 1), (3, 256, 14, 14, 1), (2, 192, 14, 14, 1),
                 (6, 512, 2, 2, 1), (4, 32, 4, 4, 1), (3, 24, 7, 7, 1), (300, 16, 7, 7, 1),
-                (3, 128, 7, 7, 2), (2, 512, 7, 7, 2), (2, 64, 14, 14, 2), (2, 256, 14, 14, 2)]
+                (3, 128, 7, 7, 2), (2, 512, 7, 7, 2), (2, 64, 14, 14, 2), (2, 256, 14, 14, 2),
+                (300, 512, 7, 7, 1)]   # more images than resident CTAs at full width: the resident-image backward (8 ring slots,
+                                       # two-round table publish, double-buffered gradient), some CTAs with a second image
 
 
 PLANAR_SHAPES = [(2, 16, 112, 112, 1), (2, 24, 56, 56, 1), (3, 40, 28, 28, 1), (2, 7, 9, 13, 1), (2, 5, 3, 3, 1),
