@@ -702,7 +702,8 @@ def test_fp32_tokens_under_autocast_take_the_token_kernels(cuda_device):
 
 
 @pytest.mark.parametrize("shape", [(5, 64, 7, 7, 1), (3, 512, 7, 7, 1), (2, 960, 7, 7, 1), (3, 256, 14, 14, 1),
-                                   (6, 512, 2, 2, 1), (3, 128, 7, 7, 2), (300, 16, 7, 7, 1)],
+                                   (6, 512, 2, 2, 1), (3, 128, 7, 7, 2), (300, 16, 7, 7, 1),
+                                   (300, 512, 7, 7, 1)],   # full width, more images than resident CTAs (resident-image backward)
                          ids=lambda s: "x".join(map(str, s[:4])) + f"_r{s[4]}")
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 def test_fused_head_matches_composition_and_oracle(shape, dtype, cuda_device):
