@@ -14,7 +14,8 @@
  *   nfpb200_pool_backward  <- autograd through those two lines
  *   nfpb200_output_shape   <- Conv2d output-size rule behind NFPPooling.output_size
  *                                                           (nfp.py:125-130, 42-47)
- *   nfpb200_desc_t         <- the constructor arguments     (nfp.py:16-18)
+ *   nfpb200_desc_t         <- the constructor arguments     (nfp.py:16-18); inner_R: the two NFP layers of
+ *                             MultiRadiusNFPHead evaluated together (models/nfp_heads.py:86-93,111-112)
  *
  * Conventions
  *   - plain C types only; every buffer is caller-owned DEVICE memory (NCHW,
@@ -181,7 +182,8 @@ int nfpb200_launch_count(const nfpb200_desc_t* desc, int32_t op, int32_t* launch
 int nfpb200_forward(const nfpb200_desc_t* desc, const void* x, void* y,
                     void* workspace, size_t workspace_bytes, void* stream);
 
-/* gx (B, C, H, W) = d<gy, NFP(x)>/dx ; similarities are recomputed from x, nothing is saved by forward. */
+/* gx (B, C, H, W) = d<gy, NFP(x)>/dx ; similarities are recomputed from x, nothing is saved by forward.
+ * (desc->inner_R = r > 0: gy is (B, K_r + K, H, W) and gx the sum of both layers' input gradients.) */
 int nfpb200_backward(const nfpb200_desc_t* desc, const void* x, const void* gy, void* gx,
                      void* workspace, size_t workspace_bytes, void* stream);
 
