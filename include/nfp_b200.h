@@ -147,8 +147,9 @@ typedef struct nfpb200_desc {
                                radius r is the inner part of the window of radius R under reflect / replicate / zero
                                padding alike, so both maps come out of ONE pass over x, and the backward folds both
                                gradient blocks into one stencil.  nfpb200_forward / nfpb200_backward on the fused
-                               (NCHW ring and channels-last token) kernels only; anything else: NFPB200_EUNSUPPORTED,
-                               and the caller issues one launch per radius */
+                               (NCHW ring, channels-last token) kernels and, for other map sizes with 16-byte aligned
+                               planes, the planar row-band kernels; anything else: NFPB200_EUNSUPPORTED, and the caller
+                               issues one launch per radius */
   int64_t x_batch_stride;   /* NHWC only: elements between consecutive images of x; 0 = dense (H*W*C); multiple of 8 */
   int64_t gx_batch_stride;  /* NHWC only: the same for gx */
 } nfpb200_desc_t;

@@ -71,7 +71,9 @@ int choose_path(const nfpb200_desc_t* d, const KParams& P, int op) {
     const int want = d->path & ~kPathFlags;
     if (want == NFPB200_PATH_GENERIC || want == NFPB200_PATH_SPLIT) return NFPB200_EUNSUPPORTED;
     if (P.layout == NFPB200_LAYOUT_NHWC) return token_supported(P, d->dtype, d->measure, op) ? 4 : NFPB200_EUNSUPPORTED;
-    return stream_supported(P, d->dtype, d->measure, op) ? 2 : NFPB200_EUNSUPPORTED;
+    if (stream_supported(P, d->dtype, d->measure, op)) return 2;
+    if (want == NFPB200_PATH_FUSED) return NFPB200_EUNSUPPORTED;
+    return planar_supported(P, d->dtype, d->measure, op) ? 3 : NFPB200_EUNSUPPORTED;   // other map sizes: row-band kernels
   }
   if (P.layout == NFPB200_LAYOUT_NHWC) {
     if ((d->path & ~kPathFlags) == NFPB200_PATH_GENERIC) return NFPB200_EUNSUPPORTED;

@@ -34,6 +34,7 @@ constexpr int kMaxR = 2;  // wider windows take the generic kernels (the unrolle
 struct PlanarParams {
   int B, C, H, W, P, mode, similarity;
   float eps;
+  int kin;  // multi-radius launch (desc.inner_R = 1 with R = 2): 8 planes of the radius-1 map in front of y / gy (band kernels)
 };
 
 template <int R>
@@ -318,6 +319,42 @@ __device__ __forceinline__ void band_dots(const unsigned char* pl, int pitch, in
   }
 }
 
+// Upstream gradient of one image as the band kernels see it.  Multi-radius launch: element (tap n, pixel) of the radius-R
+// block plus, for the inner taps, the same tap of the radius-r block in front of it (inner_tap folds to a constant in the
+// unrolled tap loops).
+template <typename T, int R>
+struct GyView {
+  const T* __restrict__ outer;
+  const T* __restrict__ inner;  // null = single radius
+  int P;
+  __device__ __forceinline__ float at(int n, int pix) const {
+    float v = to_f32(outer[(size_t)n * P + pix]);
+    if constexpr (R >= 2) {
+      if (inner) {
+        const int n1 = inner_tap(n, R, 1);
+        if (n1 >= 0) v += to_f32(inner[(size_t)n1 * P + pix]);
+      }
+    }
+    return v;
+  }
+};
+template <typename T, int R>
+__device__ __forceinline__ float folded_taps_view(const GyView<T, R>& gv, int pix, const int (&fy)[2 * R + 1],
+                                                  const int (&fx)[2 * R + 1], int oy, int ox) {
+  constexpr int k = 2 * R + 1, CTR = R * k + R;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < k; ++i)
+#pragma unroll
+    for (int j = 0; j < k; ++j) {
+      if (i * k + j != CTR && fy[i] == oy && fx[j] == ox) {
+        const int t = i * k + j;
+        s += gv.at(t < CTR ? t : t - 1, pix);
+      }
+    }
+  return s;
+}
+
 // forward values of one band pixel from its window dots: yv[n], n = tap number
 template <int R, bool INTERIOR>
 __device__ __forceinline__ void band_forward_pixel(const float (&acc)[(2 * R + 1) * (2 * R + 1)], const float* inv, int ps,
@@ -351,7 +388,7 @@ __device__ __forceinline__ void band_forward_pixel(const float (&acc)[(2 * R + 1
 // w[o] multiplies x[p + off(o)]; outside the map: 0
 template <typename T, int R, bool INTERIOR>
 __device__ __forceinline__ void band_coefficients(const float (&acc)[(2 * R + 1) * (2 * R + 1)], const float* inv, int ps, int p,
-                                                  int pr, int pc, const PlanarParams& q, const T* __restrict__ gyb, float sgn,
+                                                  int pr, int pc, const PlanarParams& q, const GyView<T, R>& gv, float sgn,
                                                   float (&w)[(2 * R + 1) * (2 * R + 1)]) {
   constexpr int k = 2 * R + 1, KK = k * k, K = KK - 1, CTR = R * k + R;
   const float t0 = acc[CTR], ip = inv[ps];
@@ -364,7 +401,7 @@ __device__ __forceinline__ void band_coefficients(const float (&acc)[(2 * R + 1)
       if (o == CTR) continue;
       const int dv = (o / k - R) * q.W + (o % k - R);
       const int n = o < CTR ? o : o - 1;  // the direct tap of p towards v, and v's direct tap back
-      const float s = to_f32(gyb[(size_t)n * q.P + p]) + to_f32(gyb[(size_t)(K - 1 - n) * q.P + p + dv]);
+      const float s = gv.at(n, p) + gv.at(K - 1 - n, p + dv);
       w[o] = sgn * s * ip * inv[ps + dv];
       s_dot = fmaf(w[o], acc[o], s_dot);
     }
@@ -382,14 +419,14 @@ __device__ __forceinline__ void band_coefficients(const float (&acc)[(2 * R + 1)
       const int v = window_pixel(pr, pc, oy - R, ox - R, q);
       w[o] = 0.f;
       if (v >= 0) {
-        const float s = folded_taps<T, R>(gyb + p, FY[R], FX[R], oy, ox, q.P) +
-                        folded_taps<T, R>(gyb + v, FY[oy], FX[ox], k - 1 - oy, k - 1 - ox, q.P);
+        const float s = folded_taps_view<T, R>(gv, p, FY[R], FX[R], oy, ox) +
+                        folded_taps_view<T, R>(gv, v, FY[oy], FX[ox], k - 1 - oy, k - 1 - ox);
         w[o] = sgn * s * ip * inv[ps + (v - p)];
         s_dot = fmaf(w[o], acc[o], s_dot);
       }
     }
     // taps of p that land on p itself (replicate padding): y = <p,p>/(N N), gradient 2 G (1/N^2 - y/(N |p|)) x_p
-    sw = 2.f * sgn * folded_taps<T, R>(gyb + p, FY[R], FX[R], R, R, q.P) * ip * ip;
+    sw = 2.f * sgn * folded_taps_view<T, R>(gv, p, FY[R], FX[R], R, R) * ip * ip;
   }
   w[CTR] = sw - rnp * (s_dot + sw * t0);
 }
@@ -444,7 +481,18 @@ __global__ void __launch_bounds__(kThreads) planar_fused_fwd_kernel(const T* __r
   float* inv = reinterpret_cast<float*>(xs + (size_t)q.C * pitch);
   band_norms<T>(xs, inv, q, r0, A, top, bot, pitch);
   const BandSplit bs(r0, TH, q.H, q.W, R);
-  T* yb0 = y + (size_t)b * K * q.P;
+  T* yb0 = y + (size_t)b * (K + q.kin) * q.P;   // multi-radius launch: kin planes of the inner radius in front
+  auto store_y = [&](const float (&yv)[K], int p) {
+#pragma unroll
+    for (int n = 0; n < K; ++n) {
+      const T v = from_f32<T>(yv[n]);
+      yb0[(size_t)(n + q.kin) * q.P + p] = v;
+      if constexpr (R >= 2) {
+        const int n1 = inner_tap(n, R, 1);   // a constant per unrolled n
+        if (n1 >= 0 && q.kin) yb0[(size_t)n1 * q.P + p] = v;
+      }
+    }
+  };
   {
     int off[KK];  // the same for every interior pixel
 #pragma unroll
@@ -456,8 +504,7 @@ __global__ void __launch_bounds__(kThreads) planar_fused_fwd_kernel(const T* __r
       float acc[KK], yv[K];
       band_dots<T, R>(xs + (size_t)ps * ESZ, pitch, q.C, off, acc);
       band_forward_pixel<R, true>(acc, inv, ps, p, pr, pc, q, yv);
-#pragma unroll
-      for (int n = 0; n < K; ++n) yb0[(size_t)n * q.P + p] = from_f32<T>(yv[n]);
+      store_y(yv, p);
     }
   }
   for (int u = threadIdx.x; u < bs.n_brd; u += blockDim.x) {
@@ -473,8 +520,7 @@ __global__ void __launch_bounds__(kThreads) planar_fused_fwd_kernel(const T* __r
     }
     band_dots<T, R>(xs + (size_t)ps * ESZ, pitch, q.C, off, acc);
     band_forward_pixel<R, false>(acc, inv, ps, p, pr, pc, q, yv);
-#pragma unroll
-    for (int n = 0; n < K; ++n) yb0[(size_t)n * q.P + p] = from_f32<T>(yv[n]);
+    store_y(yv, p);
   }
 }
 
@@ -492,7 +538,8 @@ __global__ void __launch_bounds__(kThreads) planar_fused_bwd_kernel(const T* __r
   float* inv = reinterpret_cast<float*>(xs + (size_t)q.C * pitch);
   band_norms<T>(xs, inv, q, r0, A, top, bot, pitch);
   const float sgn = q.similarity ? 1.f : -1.f;
-  const T* gyb = gy + (size_t)b * K * q.P;
+  const T* gyimg = gy + (size_t)b * (K + q.kin) * q.P;   // multi-radius launch: [kin inner planes | K planes] per image
+  const GyView<T, R> gv{gyimg + (size_t)q.kin * q.P, q.kin ? gyimg : nullptr, q.P};
   T* gxb = gx + (size_t)b * q.C * q.P;
   const BandSplit bs(r0, TH, q.H, q.W, 2 * R);
   {
@@ -506,7 +553,7 @@ __global__ void __launch_bounds__(kThreads) planar_fused_bwd_kernel(const T* __r
       float acc[KK], w[KK];
       const unsigned char* pl = xs + (size_t)ps * ESZ;
       band_dots<T, R>(pl, pitch, q.C, off, acc);
-      band_coefficients<T, R, true>(acc, inv, ps, p, pr, pc, q, gyb, sgn, w);
+      band_coefficients<T, R, true>(acc, inv, ps, p, pr, pc, q, gv, sgn, w);
       T* gp = gxb + p;
 #pragma unroll(R == 1 ? 4 : 1)
       for (int c = 0; c < q.C; ++c, pl += pitch, gp += q.P) {
@@ -530,7 +577,7 @@ __global__ void __launch_bounds__(kThreads) planar_fused_bwd_kernel(const T* __r
     }
     const unsigned char* pl = xs + (size_t)ps * ESZ;
     band_dots<T, R>(pl, pitch, q.C, off, acc);
-    band_coefficients<T, R, false>(acc, inv, ps, p, pr, pc, q, gyb, sgn, w);
+    band_coefficients<T, R, false>(acc, inv, ps, p, pr, pc, q, gv, sgn, w);
     T* gp = gxb + p;
 #pragma unroll(R == 1 ? 4 : 1)
     for (int c = 0; c < q.C; ++c, pl += pitch, gp += q.P) {
@@ -593,6 +640,7 @@ PlanarParams make(const KParams& P) {
   PlanarParams q{};
   q.B = P.B; q.C = P.C; q.H = P.H; q.W = P.W; q.P = P.H * P.W; q.mode = P.mode; q.similarity = P.similarity;
   q.eps = P.eps;
+  q.kin = P.Kin;
   return q;
 }
 inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
@@ -663,10 +711,13 @@ int backward_t(const KParams& P, const T* x, const T* gy, T* gx, const LaunchCtx
 }  // namespace
 
 bool planar_supported(const KParams& P, int dtype, int measure, int op) {
-  (void)dtype;
   if (op != NFPB200_OP_FORWARD && op != NFPB200_OP_BACKWARD) return false;
-  return measure == NFPB200_COSINE && P.stride == 1 && P.dil == 1 && P.pad == P.R && P.R <= kMaxR &&
-         P.mode != NFPB200_PAD_CIRCULAR && P.B <= 65535;
+  if (!(measure == NFPB200_COSINE && P.stride == 1 && P.dil == 1 && P.pad == P.R && P.R <= kMaxR &&
+        P.mode != NFPB200_PAD_CIRCULAR && P.B <= 65535))
+    return false;
+  // multi-radius launches (R = 2 with the radius-1 map): the one-launch band kernels only
+  if (P.rin) return P.R == 2 && P.rin == 1 && fused_plan(P, dtype == NFPB200_BF16 ? 2 : 4).ok;
+  return true;
 }
 size_t planar_workspace_bytes(const KParams& P, int dtype, int op) {
   if (fused_plan(P, dtype == NFPB200_BF16 ? 2 : 4).ok) return 0;

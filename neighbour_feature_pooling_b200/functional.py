@@ -356,7 +356,10 @@ class _NFPMultiRadius(torch.autograd.Function):
         desc = _desc_for(x, cfg, layout)
         desc.inner_R = inner_R
         Ho, Wo = _capi.output_shape(desc)
-        y_f32 = bool(y_f32) and x.dtype == torch.bfloat16
+        # bf16 x, fp32 map (autocast): the fused kernels write fp32 directly; the planar band kernels write bf16 (widened
+        # by the caller)
+        y_f32 = bool(y_f32) and x.dtype == torch.bfloat16 and \
+            _capi.describe_path(desc, _capi.OP_FORWARD).startswith("fused/")
         if y_f32:
             desc.path |= _capi.FLAG_Y_F32
         k_in = (2 * inner_R + 1) ** 2 - 1

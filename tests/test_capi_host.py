@@ -61,6 +61,10 @@ def test_multi_radius_descriptor():
     for path in ("generic", "split"):
         assert lib.nfpb200_workspace_bytes(ctypes.byref(d(path=path)), _capi.OP_FORWARD, ctypes.byref(n)) == -5
     # maps / geometries outside the fused kernels: refused (the caller launches once per radius)
+    # other map sizes with 16-byte aligned planes: the planar row-band kernels, still one launch and no workspace
+    assert _capi.describe_path(d(H=28, W=28), _capi.OP_BACKWARD) == "planar/band"
+    assert _capi.workspace_bytes(d(H=28, W=28), _capi.OP_BACKWARD) == 0 and _capi.launch_count(d(H=28, W=28), _capi.OP_FORWARD) == 1
+    assert lib.nfpb200_workspace_bytes(ctypes.byref(d(H=28, W=28, path="fused")), _capi.OP_FORWARD, ctypes.byref(n)) == -5
     for bad in (d(H=9, W=9), d(stride=2), d(measure="dot"), d(padding_mode="circular")):
         assert lib.nfpb200_workspace_bytes(ctypes.byref(bad), _capi.OP_FORWARD, ctypes.byref(n)) == -5
 

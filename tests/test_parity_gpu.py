@@ -919,6 +919,43 @@ def test_multi_radius_channels_last(shape, autocast, cuda_device):
     assert rel_err(xd.grad.float().cpu()[sl], gx_ref) < BF16_TOL
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 28, 28), (3, 12, 12, 8), (2, 8, 5, 8)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("mode,similarity", [("reflect", True), ("zeros", False), ("replicate", True)],
+                         ids=["reflect", "zeros_dist", "replicate"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_multi_radius_other_map_sizes(shape, mode, similarity, dtype, cuda_device):
+    """Maps outside the fused kernels' shape list with 16-byte aligned planes: the planar row-band kernels take the
+    multi-radius launch too (one launch each way, both gradient blocks folded into one stencil)."""
+    B, C, H, W = shape
+    gen = torch.Generator().manual_seed(B * 17 + C + H)
+    x = torch.randn(B, C, H, W, generator=gen)
+    x[0, :, 0, 0] = 0.0
+    g = torch.randn(B, 32, H, W, generator=gen)
+    if dtype == torch.bfloat16:
+        x, g = x.bfloat16().float(), g.bfloat16().float()
+    y_ref, gx_ref = _multi_ref(x, g, mode, similarity)
+    mr = nfpb.MultiRadiusNFP(C, padding_mode=mode, similarity=similarity).to(cuda_device)
+    NF.PATH_TRACE = set()
+    try:
+        xd = x.to(cuda_device, dtype).requires_grad_(True)
+        y = mr(xd)
+        y.backward(g.to(cuda_device, dtype))
+        trace = set(NF.PATH_TRACE)
+    finally:
+        NF.PATH_TRACE = None
+    assert any("radii 1+2 in one launch" in t and "planar/band" in t for t in trace), trace
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert rel_err(y.detach().float().cpu(), y_ref) < tol
+    assert rel_err(xd.grad.float().cpu(), gx_ref) < tol
+    x2 = x.to(cuda_device, dtype).requires_grad_(True)   # bit-repeatable
+    y2 = mr(x2)
+    y2.backward(g.to(cuda_device, dtype))
+    assert torch.equal(y2, y) and torch.equal(x2.grad, xd.grad)
+    if dtype == torch.bfloat16:   # under autocast the map is fp32 (the band kernels' bf16 result is widened)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            assert mr(x2.detach()).dtype == torch.float32
+
+
 def test_multi_radius_fallbacks_and_head_fusion(cuda_device):
     """(a) configurations the one-launch form does not cover are computed layer by layer + cat (same values);
     (b) fuse_multi_radius() on a ModuleList built exactly like MultiRadiusNFPHead.nfp_blocks (nfp_heads.py:86-93): the
